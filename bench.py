@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py - rendered views/sec of the tri-plane volumetric renderer hot path.
+
+Workload (BASELINE.json configs[1]): per GPU a batch of 8 views, 128x128 rays, 96 coarse + 96
+importance samples per ray, 8 distinct 3x32x512x512 fp32 tri-planes, OSGDecoder 32->64->33.
+A "step" = one pass of the hot path over that batch: layout pre-pass (NCHW -> channels-last
+texels) + ray generation + ImportanceRenderer.forward.  Synthetic data, random-init decoder.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]           our arm (CUDA, one rank per GPU)
+    python bench.py --impl reference [...]                        the reference's CPU algorithm (oracle port)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section "Measurement" for how every field is derived.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'rendered views/sec @128x128 rays x96 samples, 512^2x32ch tri-plane'
+UNIT = 'views/s'
+R, S, SF, P, C, VIEWS = 128, 96, 96, 512, 32, 8
+FLOP_PER_SAMPLE = 2 * 32 * 64 + 2 * 64 * 33            # 8,320 tensor-eligible FLOP
+BYTES_PER_VIEW = 3 * C * P * P * 4 + R * R * 37 * 4    # tri-plane read once + 37 floats/ray out
+
+
+def workload_config(n_gpus, mlp_mode='fp32_simt'):
+    return {'workload': f'{VIEWS} views/GPU x {R}x{R} rays x ({S}+{SF}) samples, {VIEWS} distinct 3x{C}x{P}x{P} fp32 tri-planes/GPU',
+            'views_per_gpu': VIEWS, 'rays': R * R, 'samples_coarse': S, 'samples_importance': SF, 'plane': P,
+            'decoder': '32-64-33 softplus', 'mlp_mode': mlp_mode, 'parallelism': f'views sharded x{n_gpus}',
+            'l2': 'inputs (805 MB planes + 3.4 GB scratch per step) exceed the 126 MB L2; no explicit flush'}
+
+
+def read_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            pk = json.load(f)
+        return pk['hbm_gbs'], pk.get('bf16_tflops_sustained', pk['bf16_tflops']), 'measured (MEASURED_PEAKS.json, sustained)'
+    except Exception:
+        return 6650.0, 1400.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            self.t.join(timeout=5)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        busy = sorted(sm)[len(sm) // 2:]      # upper half = samples under load
+        return {'sm_mhz': statistics.median(busy), 'sm_max_mhz': max(mx), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port (torch CPU, the reference's own ATen op chain)
+# --------------------------------------------------------------------------------------------
+def cpu_reference_time(steps, warmup, views=1):
+    """Times oracle.render (gather='aten') on `views` view(s) of the bench workload per step."""
+    import torch
+    from oracle import renderer_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    planes = torch.randn(views, 3, C, P, P, generator=g)
+    dec = dict(w1=torch.randn(64, C, generator=g), b1=torch.zeros(64), w2=torch.randn(33, 64, generator=g), b2=torch.zeros(33),
+               lr_mul=1.0, force_sigmoid=False)
+    cams = [orc.camera_params_to_matrix(0.0, -180.0 + 30.0 * i, 1.0, 30.0) for i in range(views)]
+    c2w, K = torch.stack([c[0] for c in cams]), torch.stack([c[1] for c in cams])
+    opts = dict(orc.DEFAULT_OPTS)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            u_c = torch.rand(views, R * R, S, 1, generator=g)
+            u_f = torch.rand(views * R * R, SF, generator=g)
+            t0 = time.perf_counter()
+            ro, rd = orc.ray_sampler(c2w, K, R)
+            orc.render(planes, dec, ro, rd, opts, u_c, u_f, use_triplane=True, gather='aten')
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    times, cores = cpu_reference_time(steps, warmup, views=1)
+    total = sum(times)
+    v = len(times) / total
+    sample = f'{len(times)} timed steps x 1 view of the workload (128x128 rays, 96+96 samples, 512^2 planes) after {warmup} warm-up'
+    out = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(times),
+           'warmup': warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.gpus, 'cpu'),
+           'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+           'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
+    print(json.dumps(out), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes as Ct
+    import torch
+    import torch.distributed as dist
+    import panic3d_b200  # noqa: F401
+    from panic3d_b200 import _lib, cameras
+    from panic3d_b200.training.volumetric_rendering.renderer import ImportanceRenderer
+    from panic3d_b200.training.volumetric_rendering.ray_sampler import RaySampler
+    from panic3d_b200.training.triplane import OSGDecoder
+    from oracle import renderer_oracle as orc      # DEFAULT_OPTS table + (rank 0, N=1) the cpu_baseline leg
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    L = _lib.lib()
+
+    mlp_mode = {'fp32_simt': 0, 'tc_3xbf16': 1, 'tc_bf16': 2}[args.mlp]
+    torch.manual_seed(1234 + rank)
+    planes = torch.randn(VIEWS, 3, C, P, P, device=dev)                         # NCHW fp32, as the backbone emits
+    decoder = OSGDecoder(C, {'decoder_lr_mul': 1, 'decoder_output_dim': 32}).to(dev).requires_grad_(False)
+    spin = cameras.cam60[cameras.camsubs['spin12']]
+    labels = torch.stack([cameras.camera_params_to_matrix(elev=float(spin[(rank * VIEWS + i) % 12][0]),
+                                                          azim=float(spin[(rank * VIEWS + i) % 12][1]), dist=1.0, fov=30.0)['camera_label']
+                          for i in range(VIEWS)])
+    labels_dev = labels.to(dev)
+    opts = dict(orc.DEFAULT_OPTS)
+    renderer, sampler = ImportanceRenderer(use_triplane=True), RaySampler()
+    renderer.mlp_mode = mlp_mode
+    gather_buf = torch.empty((world * VIEWS, R * R, 32), device=dev) if world > 1 else None
+
+    def step():
+        c2w, K = labels_dev[:, :16].view(-1, 4, 4), labels_dev[:, 16:25].view(-1, 3, 3)
+        ro, rd = sampler(c2w, K, R)
+        renderer._planes.key = None                                           # distinct tri-planes every step: redo the layout pass
+        rgb, depth, wsum, xyz = renderer(planes, decoder, ro, rd, opts)
+        if world > 1:                                                            # rendered images -> every rank (rank 0 consumes them)
+            dist.all_gather_into_tensor(gather_buf, rgb)
+        return rgb
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step()
+        barrier()
+        # ---- timed region: device time (CUDA events on the launching stream), max over ranks
+        L.p3d_profile_read(None, None, 0, 1)
+        n0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            barrier()
+            e0.record()
+            for _ in range(args.steps):
+                step()
+            e1.record()
+            barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - n0
+        # ---- per-kernel device time for the roofline (separate short run with event brackets enabled)
+        L.p3d_profile_enable(1)
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        slot_ms = (Ct.c_double * 8)()
+        slot_n = (Ct.c_uint64 * 8)()
+        L.p3d_profile_read(slot_ms, slot_n, 8, 1)
+        L.p3d_profile_enable(0)
+        # ---- e2e through the host-buffer C-ABI entry point (pinned host planes in, images out)
+        e2e = None
+        if not args.no_e2e:
+            e2e = run_e2e(L, _lib, planes, decoder, labels, opts, mlp_mode, args, barrier)
+
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    if e2e is not None:
+        te = torch.tensor([e2e['ms']], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e['ms'] = float(te.item())
+    clocks = clk.summary()
+
+    if rank == 0:
+        value = world * VIEWS * args.steps / (ms_max * 1e-3)
+        hbm_gbs, tc_tf, peak_src = read_peaks()
+        fused = slot_n[5] > 0
+        slot = 5 if fused else 0
+        kern_ms = slot_ms[slot] / max(1, slot_n[slot])                         # avg duration of ONE launch of the dominant kernel
+        samples_per_launch = VIEWS * R * R * (S + SF) / (1 if fused else 2)     # v1: coarse and fine are separate launches
+        flops = FLOP_PER_SAMPLE * samples_per_launch
+        byts = BYTES_PER_VIEW * VIEWS / (1 if fused else 2)
+        t_tensor, t_hbm = flops / (tc_tf * 1e12), byts / (hbm_gbs * 1e9)
+        if t_tensor >= t_hbm:
+            roof = {'bound': 'tensor', 'achieved': flops / (kern_ms * 1e-3) / 1e12, 'peak': tc_tf, 'unit': 'TFLOP/s'}
+        else:
+            roof = {'bound': 'hbm', 'achieved': byts / (kern_ms * 1e-3) / 1e9, 'peak': hbm_gbs, 'unit': 'GB/s'}
+        roof.update({'frac': roof['achieved'] / roof['peak'], 'traffic': None,
+                     'kernel': 'k_render_fused' if fused else 'k_sample_decode', 'kernel_ms_per_launch': kern_ms,
+                     'launches_timed': int(slot_n[slot]), 'peak_source': peak_src,
+                     'step_breakdown_ms': {'sample_decode': slot_ms[0] / 3, 'importance': slot_ms[1] / 3, 'composite': slot_ms[2] / 3,
+                                           'layout': slot_ms[3] / 3, 'raygen': slot_ms[4] / 3, 'fused': slot_ms[5] / 3}})
+        out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+               'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+               'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world, args.mlp), 'clocks': clocks,
+               'gpu_launches': int(launches), 'roofline': roof}
+        if e2e is not None:
+            out['e2e'] = {'value': world * VIEWS * e2e['steps'] / (e2e['ms'] * 1e-3), 'unit': UNIT,
+                          'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'], 'steps': e2e['steps'],
+                          'api': 'p3d_render_forward_host (C-ABI, pinned host buffers)'}
+        if world == 1 and not args.no_cpu_baseline:
+            times, cores = cpu_reference_time(steps=3, warmup=1, views=1)
+            out['cpu_baseline'] = {'value': len(times) / sum(times), 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                   'sample': '3 timed renders of 1 view of the same workload (oracle port, torch CPU, all cores) after 1 warm-up'}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(L, _lib, planes, decoder, labels, opts, mlp_mode, args, barrier):
+    """Same step through p3d_render_forward_host: NCHW planes, decoder and cameras start in pinned HOST memory,
+    results land in pinned host memory; H2D and D2H copies are inside the timed region every step."""
+    import ctypes as Ct
+    import torch
+    p = _lib.RenderParams()
+    p.n_views, p.n_rays, p.n_coarse, p.n_fine = VIEWS, R * R, S, SF
+    p.channels, p.plane_h, p.plane_w, p.hidden, p.out_dim = C, P, P, 64, 33
+    p.box_warp, p.ray_start, p.ray_end = opts['box_warp'], opts['ray_start'], opts['ray_end']
+    p.ray_mode, p.disparity, p.white_back, p.plane_mode = 0, 0, 1, 1
+    fc1, fc2 = decoder.net[0], decoder.net[2]
+    p.w1_gain, p.b1_gain, p.w2_gain, p.b2_gain = float(fc1.weight_gain), float(fc1.bias_gain), float(fc2.weight_gain), float(fc2.bias_gain)
+    p.mlp_mode, p.seed = mlp_mode, 7
+    h_planes = planes.cpu().pin_memory()
+    h_w = [t.detach().cpu().float().contiguous().pin_memory() for t in (fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
+    h_c2w = labels[:, :16].contiguous().pin_memory()
+    h_K = labels[:, 16:25].contiguous().pin_memory()
+    outs = [torch.empty(s, dtype=torch.float32).pin_memory() for s in ((VIEWS, R * R, 32), (VIEWS, R * R), (VIEWS, R * R), (VIEWS, R * R, 3))]
+
+    def call():
+        _lib.check(L.p3d_render_forward_host(Ct.byref(p), h_planes.data_ptr(), *[w.data_ptr() for w in h_w], h_c2w.data_ptr(),
+                                             h_K.data_ptr(), R, None, None, *[o.data_ptr() for o in outs]))
+    for _ in range(2):
+        call()
+    steps = max(1, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()                                     # synchronises internally (results are on the host when it returns)
+    ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    L.p3d_host_arena_release()
+    h2d = h_planes.numel() * 4 + sum(w.numel() for w in h_w) * 4 + (h_c2w.numel() + h_K.numel()) * 4
+    d2h = sum(o.numel() for o in outs) * 4
+    return {'ms': ms, 'steps': steps, 'h2d': h2d, 'd2h': d2h}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--mlp', default=os.environ.get('P3D_BENCH_MLP', 'fp32_simt'), choices=['fp32_simt', 'tc_3xbf16', 'tc_bf16'])
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        world = int(os.environ.get('WORLD_SIZE', '1'))
+        if world != args.gpus and args.gpus > 1 and world == 1:
+            raise SystemExit('--gpus N>1 must be launched with torch.distributed.run (one rank per GPU)')
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,156 @@
+/*
+ * p3d_render.h - C ABI of the B200-native tri-plane volumetric renderer.
+ *
+ * Drop-in boundary for the hot path of panic3d's EG3D-derived ray-marcher.  The
+ * reference has NO native code on this path (it is ~60 eager PyTorch ops per
+ * pass); each entry point below names the reference
+ * Python interface it replaces (paths relative to
+ * /root/reference/_train/eg3dc/src/training/).  Everything is plain C: device
+ * (or, for the *_host entry points, host) pointers + sizes + a cudaStream_t
+ * passed as void*.  No torch types cross this boundary.
+ *
+ * Conventions
+ *   - all tensors fp32 unless stated; "device pointer" means memory of the
+ *     CUDA device that is current on the calling thread;
+ *   - every function returns 0 on success, a negative P3D_E* code otherwise;
+ *     p3d_last_error() returns a thread-local human-readable message
+ *     (the Python host turns it into RuntimeError, matching TORCH_CHECK);
+ *   - kernels are enqueued on `stream` and the call returns without
+ *     synchronising, except the *_host entry points which synchronise.
+ */
+#ifndef P3D_RENDER_H_
+#define P3D_RENDER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define P3D_OK            0
+#define P3D_EINVAL       -1   /* bad argument (shape, null pointer, unsupported option) */
+#define P3D_ECUDA        -2   /* CUDA runtime error (message has cudaGetErrorString) */
+#define P3D_EWORKSPACE   -3   /* workspace too small */
+#define P3D_EUNSUPPORTED -4   /* configuration has no kernel (caller must not fall back silently) */
+
+/* third tri-plane convention: generate_planes(use_triplane), volumetric_rendering/renderer.py:26-50 */
+#define P3D_PLANES_EG3D     0  /* planes read (x,y), (x,z), (z,x) */
+#define P3D_PLANES_PANIC3D  1  /* planes read (x,y), (x,z), (y,z)   [use_triplane=True] */
+
+/* ray limit mode: rendering_options['ray_start'/'ray_end'], renderer.py:165-174 */
+#define P3D_RAYS_NUMERIC 0
+#define P3D_RAYS_AUTOBOX 1     /* 'auto': math_utils.get_ray_limits_box, math_utils.py:46-98 */
+
+/* decoder arithmetic */
+#define P3D_MLP_FP32_SIMT   0  /* scalar FFMA, bit-for-bit-class fp32 (parity reference kernel) */
+#define P3D_MLP_TC_3XBF16   1  /* tcgen05 bf16 tensor cores, 3-pass split operands (fp32-class accuracy) */
+#define P3D_MLP_TC_BF16     2  /* tcgen05 bf16 single pass (fast mode; ~1e-2 abs) */
+
+typedef struct p3d_render_params {
+    /* problem size */
+    int32_t n_views;          /* N */
+    int32_t n_rays;           /* M rays per view */
+    int32_t n_coarse;         /* S  = rendering_options['depth_resolution'] */
+    int32_t n_fine;           /* Sf = rendering_options['depth_resolution_importance'] (0 = no importance pass) */
+    int32_t channels;         /* C features per plane (32) */
+    int32_t plane_h, plane_w; /* H, W of each plane */
+    int32_t hidden;           /* OSGDecoder hidden width (64) */
+    int32_t out_dim;          /* 1 + decoder_output_dim (33): [sigma, rgb...] */
+    /* plane addressing, in ELEMENTS; channel stride must be 1 (channels-last texels).
+       stride_view may be 0 (all views share one tri-plane). */
+    int64_t stride_view, stride_plane, stride_row, stride_col;
+    int32_t planes_bf16;      /* 0: planes are fp32, 1: planes are bf16 (fast mode storage) */
+    /* rendering_options (doubles: the reference holds them as Python floats and rounds derived
+       scalars such as 2/box_warp or (ray_end-ray_start)/(S-1) to fp32 only after computing them
+       in double; the library does the same) */
+    double  box_warp;
+    double  ray_start, ray_end;
+    int32_t ray_mode;         /* P3D_RAYS_* */
+    int32_t disparity;        /* disparity_space_sampling */
+    int32_t white_back;
+    int32_t plane_mode;       /* P3D_PLANES_* */
+    /* per-call flags of ImportanceRenderer.forward (renderer.py:162) ; <= 0 disables */
+    double  triplane_crop, cull_clouds, binarize_clouds;
+    /* decoder (triplane.py:516-548): gains of FullyConnectedLayer (networks_stylegan2.py:115-128) */
+    float   w1_gain, b1_gain, w2_gain, b2_gain;
+    int32_t force_sigmoid;
+    int32_t mlp_mode;         /* P3D_MLP_* */
+    /* jitter: when the u_* pointers passed to the call are NULL, uniforms come from Philox(seed) */
+    uint64_t seed;
+} p3d_render_params;
+
+const char* p3d_version(void);
+const char* p3d_last_error(void);
+
+/* planes (N*3, C, H, W) fp32 NCHW  ->  (N*3, H, W, C) channels-last texels, fp32 or bf16.
+   Replaces nothing in the reference (it samples NCHW through F.grid_sample, renderer.py:68-81);
+   this is the layout pre-pass that makes every bilinear tap one contiguous 128 B (64 B) line. */
+int p3d_planes_to_channels_last(const float* planes_nchw, void* planes_cl, int64_t n_planes,
+                                int32_t channels, int32_t h, int32_t w, int32_t out_bf16, void* stream);
+
+/* RaySampler.forward, volumetric_rendering/ray_sampler.py:24-63.
+   cam2world (N,4,4), intrinsics (N,3,3) -> ray_origins, ray_dirs (N, R*R, 3). */
+int p3d_raygen_pinhole(const float* cam2world, const float* intrinsics, int32_t n_views, int32_t resolution,
+                       float* ray_origins, float* ray_dirs, void* stream);
+
+/* get_rays_ortho, /root/reference/_databacks/lustrous_renders_v1.py:78-104.
+   rot (N,3,3) row-major rotation (scipy Rotation 'xyz' [-elev, azim, 0] built by the host),
+   dist (N) -> ray_origins, ray_dirs (N, R*R, 3). */
+int p3d_raygen_ortho(const float* rot, const float* dist, int32_t n_views, int32_t resolution, double box_warp,
+                     float* ray_origins, float* ray_dirs, void* stream);
+
+/* Scratch needed by p3d_render_forward for these params (bytes). */
+size_t p3d_render_workspace_bytes(const p3d_render_params* p);
+
+/* ImportanceRenderer.forward, volumetric_rendering/renderer.py:162-264
+   (= sample_stratified :303-326, run_model :266-280 [sample_from_planes :68-81 + OSGDecoder
+   triplane.py:528-544], crop/cull masks :138-153, MipRayMarcher2 ray_marcher.py:25-57,
+   sample_importance :328-387, unify_samples :289-301, final composite :250-253).
+     planes      channels-last texels addressed by the strides in *p
+     w1 (hidden,C)  b1 (hidden)  w2 (out_dim,hidden)  b2 (out_dim)     raw parameters; gains in *p
+     ray_origins, ray_dirs (N,M,3)
+     u_coarse (N,M,S) or NULL, u_fine (N*M,Sf) or NULL                  injected U[0,1) jitter
+     out_rgb (N,M,out_dim-1)  out_depth (N,M)  out_wsum (N,M)  out_xyz (N,M,3)                   */
+int p3d_render_forward(const p3d_render_params* p, const void* planes,
+                       const float* w1, const float* b1, const float* w2, const float* b2,
+                       const float* ray_origins, const float* ray_dirs,
+                       const float* u_coarse, const float* u_fine,
+                       void* workspace, size_t workspace_bytes,
+                       float* out_rgb, float* out_depth, float* out_wsum, float* out_xyz, void* stream);
+
+/* ImportanceRenderer.run_model, renderer.py:266-280 (used by TriPlaneGenerator.sample /
+   sample_mixed, triplane.py:254-298, and the 256^3 grid query of _util/eg3d_metrics3d.py:94-183).
+     coords (N,K,3) -> out_rgb (N,K,out_dim-1), out_sigma (N,K).  Uses n_views and the plane /
+     decoder fields of *p; ray fields are ignored. */
+int p3d_decode_points(const p3d_render_params* p, const void* planes,
+                      const float* w1, const float* b1, const float* w2, const float* b2,
+                      const float* coords, int64_t n_points_per_view,
+                      float* out_rgb, float* out_sigma, void* stream);
+
+/* End-to-end entry point with HOST buffers (what a non-torch caller binds): copies the
+   NCHW fp32 tri-planes, decoder and cameras to the device, generates pinhole rays, renders and
+   copies (rgb, depth, wsum, xyz) back.  Device buffers are cached between calls in a
+   process-wide arena; p3d_host_arena_release() frees it.  planes_nchw (N,3,C,H,W);
+   stride fields of *p are ignored (set internally). u_* may be NULL (Philox). Synchronises. */
+int p3d_render_forward_host(const p3d_render_params* p, const float* planes_nchw,
+                            const float* w1, const float* b1, const float* w2, const float* b2,
+                            const float* cam2world, const float* intrinsics, int32_t resolution,
+                            const float* u_coarse, const float* u_fine,
+                            float* out_rgb, float* out_depth, float* out_wsum, float* out_xyz);
+void p3d_host_arena_release(void);
+
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+uint64_t p3d_launch_count(void);
+
+/* Per-kernel device timing for bench.py's roofline leg.  When enabled, launch sites bracket their
+   kernel with CUDA events on the launching stream.  Slots: 0 sample_decode (gather+MLP), 1 importance,
+   2 composite, 3 layout pre-pass, 4 raygen, 5 fused renderer, 6 other.  p3d_profile_read waits for the
+   recorded events, adds them up per slot (milliseconds, launch counts) and optionally resets. */
+void p3d_profile_enable(int on);
+int  p3d_profile_read(double* ms_by_slot, uint64_t* launches_by_slot, int n_slots, int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3D_RENDER_H_ */

@@ -1,0 +1,393 @@
+// extern "C" surface of libp3d.so (see include/p3d_render.h) + small utility kernels.
+#include <stdarg.h>
+#include <string.h>
+#include <mutex>
+#include <vector>
+
+#include "render_internal.cuh"
+
+namespace p3d {
+
+std::atomic<uint64_t> g_launches{0};
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// ------------------------------------------------------------------------------------------
+// profiler
+// ------------------------------------------------------------------------------------------
+struct ProfRec { int slot; cudaEvent_t a, b; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof_pending;
+static std::vector<cudaEvent_t> g_prof_pool;
+static double g_prof_ms[PROF_SLOTS] = {0};
+static uint64_t g_prof_n[PROF_SLOTS] = {0};
+static cudaEvent_t g_prof_open[PROF_SLOTS] = {nullptr};
+
+bool profile_enabled() { return g_prof_on; }
+static cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void profile_begin(int slot, cudaStream_t stream) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, stream);
+    g_prof_open[slot] = e;
+}
+void profile_end(int slot, cudaStream_t stream) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    cudaEvent_t e = prof_event();
+    cudaEventRecord(e, stream);
+    g_prof_pending.push_back({slot, g_prof_open[slot], e});
+    g_prof_open[slot] = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------
+// derived scalars: computed in double from the Python-side doubles, then rounded to fp32 once,
+// exactly where the reference's Python scalars meet an fp32 tensor.
+// ------------------------------------------------------------------------------------------
+int make_geom(const p3d_render_params* p, Geom* g) {
+    P3D_REQUIRE(p != nullptr, "params is NULL");
+    P3D_REQUIRE(p->channels == kC && p->hidden == kHidden && p->out_dim == kOut,
+                "decoder shape %d->%d->%d unsupported (built for %d->%d->%d)", p->channels, p->hidden, p->out_dim, kC,
+                kHidden, kOut);
+    P3D_REQUIRE(p->n_views >= 0 && p->n_rays >= 0 && p->plane_h > 0 && p->plane_w > 0, "bad sizes");
+    P3D_REQUIRE(p->box_warp > 0, "box_warp must be > 0");
+    memset(g, 0, sizeof(*g));
+    g->N = p->n_views; g->M = p->n_rays; g->S = p->n_coarse; g->Sf = p->n_fine; g->H = p->plane_h; g->W = p->plane_w;
+    g->stride_view = p->stride_view; g->stride_plane = p->stride_plane; g->stride_row = p->stride_row; g->stride_col = p->stride_col;
+    const int align = p->planes_bf16 ? 4 : 4;   // quads of 4 channels: 16 B (fp32) / 8 B (bf16) vector loads
+    P3D_REQUIRE(p->stride_view % align == 0 && p->stride_plane % align == 0 && p->stride_row % align == 0 && p->stride_col % align == 0,
+                "plane strides must be multiples of 4 elements");
+    g->coord_scale = (float)(2.0 / p->box_warp);
+    g->half_box = (float)(p->box_warp / 2.0);
+    g->ray_mode = p->ray_mode; g->disparity = p->disparity; g->white_back = p->white_back; g->plane_mode = p->plane_mode;
+    if (p->ray_mode == P3D_RAYS_NUMERIC) {
+        g->ray_start = (float)p->ray_start; g->ray_end = (float)p->ray_end;
+        const int S = p->n_coarse > 1 ? p->n_coarse : 2;
+        g->lin_step = (g->ray_end - g->ray_start) / (float)(S - 1);                  // torch.linspace: fp32 step
+        g->depth_delta = (float)((p->ray_end - p->ray_start) / (double)(S - 1));      // python double -> fp32
+        g->inv_start = (float)(1.0 / p->ray_start); g->inv_end = (float)(1.0 / p->ray_end);
+        g->disp_delta = (float)(1.0 / (double)(S - 1));
+    }
+    g->crop_on = p->triplane_crop > 0; g->crop_limit = (float)(p->box_warp / 2.0 - p->triplane_crop);
+    g->binarize_on = p->binarize_clouds > 0; g->cull_on = !g->binarize_on && p->cull_clouds > 0;
+    g->cull_thresh = (float)(g->binarize_on ? p->binarize_clouds : p->cull_clouds);
+    g->force_sigmoid = p->force_sigmoid;
+    g->w1_gain = p->w1_gain; g->b1_gain = p->b1_gain; g->w2_gain = p->w2_gain; g->b2_gain = p->b2_gain;
+    g->seed = p->seed;
+    return P3D_OK;
+}
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t workspace_layout(const p3d_render_params* p, void* base, Workspace* ws) {
+    const size_t R = (size_t)p->n_views * (size_t)p->n_rays;
+    const size_t S = (size_t)p->n_coarse, Sf = (size_t)p->n_fine;
+    size_t off = 0;
+    char* b = reinterpret_cast<char*>(base);
+    auto take = [&](size_t bytes) { void* ptr = b ? b + off : nullptr; off += align_up(bytes); return ptr; };
+    Workspace w;
+    w.bounds = (unsigned int*)take(64);
+    w.depth_c = (float*)take(R * S * 4);
+    w.sigma_c = (float*)take(R * S * 4);
+    w.rgb_c = (float*)take(R * S * kRgb * 4);
+    w.depth_f = (float*)take(R * Sf * 4);
+    w.sigma_f = (float*)take(R * Sf * 4);
+    w.rgb_f = (float*)take(R * Sf * kRgb * 4);
+    w.ray_t0 = (float*)take(R * 4);
+    w.ray_t1 = (float*)take(R * 4);
+    if (ws) *ws = w;
+    return off;
+}
+
+// ------------------------------------------------------------------------------------------
+// layout pre-pass: (n_planes, C, H, W) fp32 -> (n_planes, H, W, C) fp32|bf16.  32x32 smem transpose.
+// ------------------------------------------------------------------------------------------
+template <bool BF16>
+__global__ void k_planes_to_cl(const float* __restrict__ in, void* __restrict__ out, int C, long long HW) {
+    __shared__ float tile[32][33];
+    const long long plane = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;     // pixel tile
+    const int c0 = blockIdx.y * 32;                      // channel tile
+    const int tx = threadIdx.x, ty = threadIdx.y;        // 32 x 8
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r;
+        const long long px = p0 + tx;
+        tile[r][tx] = (c < C && px < HW) ? in[(plane * C + c) * HW + px] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const long long px = p0 + r;
+        const int c = c0 + tx;
+        if (c < C && px < HW) {
+            const long long o = (plane * HW + px) * C + c;
+            if (BF16) reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16_rn(tile[tx][r]);
+            else reinterpret_cast<float*>(out)[o] = tile[tx][r];
+        }
+    }
+}
+
+// RaySampler.forward, ray_sampler.py:24-63
+__global__ void k_raygen_pinhole(const float* __restrict__ c2w, const float* __restrict__ K, int N, int R,
+                                 float* __restrict__ ro, float* __restrict__ rd) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long M = (long long)R * R;
+    if (idx >= (long long)N * M) return;
+    const int n = (int)(idx / M);
+    const int m = (int)(idx - (long long)n * M);
+    const int row = m / R, col = m - row * R;
+    const float* k = K + n * 9;
+    const float* c = c2w + n * 16;
+    const float fx = k[0], sk = k[1], cx = k[2], fy = k[4], cy = k[5];
+    const float inv_r = __fdiv_rn(1.f, (float)R), half = __fdiv_rn(0.5f, (float)R);
+    const float xc = __fadd_rn(__fmul_rn((float)col, inv_r), half);
+    const float yc = __fadd_rn(__fmul_rn((float)row, inv_r), half);
+    // (x - cx + cy*sk/fy - sk*y/fy) / fx , (y - cy) / fy      (z_cam = 1)
+    float xl = __fsub_rn(xc, cx);
+    xl = __fadd_rn(xl, __fdiv_rn(__fmul_rn(cy, sk), fy));
+    xl = __fsub_rn(xl, __fdiv_rn(__fmul_rn(sk, yc), fy));
+    xl = __fdiv_rn(xl, fx);
+    const float yl = __fdiv_rn(__fsub_rn(yc, cy), fy);
+    float d[3], o[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float w = fmaf(c[i * 4 + 0], xl, fmaf(c[i * 4 + 1], yl, c[i * 4 + 2])) + c[i * 4 + 3];
+        o[i] = c[i * 4 + 3];
+        d[i] = __fsub_rn(w, o[i]);
+    }
+    const float nrm = fmaxf(sqrtf(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]), 1e-12f);   // F.normalize eps
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { ro[idx * 3 + i] = o[i]; rd[idx * 3 + i] = __fdiv_rn(d[i], nrm); }
+}
+
+// get_rays_ortho, lustrous_renders_v1.py:78-104
+__global__ void k_raygen_ortho(const float* __restrict__ rot, const float* __restrict__ dist, int N, int R, float bw,
+                               float* __restrict__ ro, float* __restrict__ rd) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long M = (long long)R * R;
+    if (idx >= (long long)N * M) return;
+    const int n = (int)(idx / M);
+    const int m = (int)(idx - (long long)n * M);
+    const int row = m / R, col = m - row * R;
+    const float half = __fdiv_rn(bw, 2.f);
+    const float gx = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)col, 0.5f), (float)R), bw), half);
+    const float gy = -__fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn((float)row, 0.5f), (float)R), bw), half);
+    const float z0 = dist[n], z1 = __fadd_rn(-1.f, dist[n]);
+    const float* r = rot + n * 9;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const float a = r[i * 3 + 0] * gx + r[i * 3 + 1] * gy;
+        const float p0 = a + r[i * 3 + 2] * z0, p1 = a + r[i * 3 + 2] * z1;
+        ro[idx * 3 + i] = p0;
+        rd[idx * 3 + i] = __fsub_rn(p1, p0);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host arena for the *_host entry point
+// ------------------------------------------------------------------------------------------
+struct Arena {
+    std::mutex mu;
+    std::vector<std::pair<void*, size_t>> bufs;   // slot -> (ptr, bytes)
+    cudaStream_t stream = nullptr;
+    int get(size_t slot, size_t bytes, void** out) {
+        if (bufs.size() <= slot) bufs.resize(slot + 1, {nullptr, 0});
+        if (bufs[slot].second < bytes) {
+            if (bufs[slot].first) cudaFree(bufs[slot].first);
+            bufs[slot] = {nullptr, 0};
+            P3D_CUDA_TRY(cudaMalloc(&bufs[slot].first, bytes));
+            bufs[slot].second = bytes;
+        }
+        *out = bufs[slot].first;
+        return P3D_OK;
+    }
+    void release() {
+        for (auto& b : bufs) if (b.first) cudaFree(b.first);
+        bufs.clear();
+        if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+    }
+};
+static Arena g_arena;
+
+}  // namespace p3d
+
+using namespace p3d;
+
+extern "C" {
+
+const char* p3d_version(void) { return "p3d-render-b200 0.1 (sm_100a)"; }
+const char* p3d_last_error(void) { return g_err; }
+uint64_t p3d_launch_count(void) { return g_launches.load(); }
+
+int p3d_planes_to_channels_last(const float* planes_nchw, void* planes_cl, int64_t n_planes, int32_t channels,
+                                int32_t h, int32_t w, int32_t out_bf16, void* stream) {
+    P3D_REQUIRE(planes_nchw && planes_cl, "null plane pointer");
+    P3D_REQUIRE(n_planes >= 0 && n_planes < 65536 && channels > 0 && h > 0 && w > 0, "bad plane sizes");
+    if (n_planes == 0) return P3D_OK;
+    const long long HW = (long long)h * w;
+    dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((channels + 31) / 32), (unsigned)n_planes), block(32, 8);
+    ProfileScope prof(PROF_LAYOUT, (cudaStream_t)stream);
+    if (out_bf16) k_planes_to_cl<true><<<grid, block, 0, (cudaStream_t)stream>>>(planes_nchw, planes_cl, channels, HW);
+    else k_planes_to_cl<false><<<grid, block, 0, (cudaStream_t)stream>>>(planes_nchw, planes_cl, channels, HW);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+}
+
+int p3d_raygen_pinhole(const float* cam2world, const float* intrinsics, int32_t n_views, int32_t resolution,
+                       float* ray_origins, float* ray_dirs, void* stream) {
+    P3D_REQUIRE(cam2world && intrinsics && ray_origins && ray_dirs, "null pointer");
+    P3D_REQUIRE(n_views >= 0 && resolution > 0, "bad sizes");
+    const long long total = (long long)n_views * resolution * resolution;
+    if (total == 0) return P3D_OK;
+    ProfileScope prof(PROF_RAYGEN, (cudaStream_t)stream);
+    k_raygen_pinhole<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(cam2world, intrinsics, n_views,
+                                                                                        resolution, ray_origins, ray_dirs);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+}
+
+int p3d_raygen_ortho(const float* rot, const float* dist, int32_t n_views, int32_t resolution, double box_warp,
+                     float* ray_origins, float* ray_dirs, void* stream) {
+    P3D_REQUIRE(rot && dist && ray_origins && ray_dirs, "null pointer");
+    P3D_REQUIRE(n_views >= 0 && resolution > 0, "bad sizes");
+    const long long total = (long long)n_views * resolution * resolution;
+    if (total == 0) return P3D_OK;
+    k_raygen_ortho<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rot, dist, n_views, resolution,
+                                                                                      (float)box_warp, ray_origins, ray_dirs);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+}
+
+void p3d_profile_enable(int on) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    g_prof_on = on != 0;
+}
+
+int p3d_profile_read(double* ms_by_slot, uint64_t* launches_by_slot, int n_slots, int reset) {
+    std::lock_guard<std::mutex> l(g_prof_mu);
+    for (auto& r : g_prof_pending) {
+        P3D_CUDA_TRY(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        P3D_CUDA_TRY(cudaEventElapsedTime(&ms, r.a, r.b));
+        g_prof_ms[r.slot] += ms; g_prof_n[r.slot] += 1;
+        g_prof_pool.push_back(r.a); g_prof_pool.push_back(r.b);
+    }
+    g_prof_pending.clear();
+    for (int i = 0; i < n_slots && i < PROF_SLOTS; ++i) {
+        if (ms_by_slot) ms_by_slot[i] = g_prof_ms[i];
+        if (launches_by_slot) launches_by_slot[i] = g_prof_n[i];
+    }
+    if (reset) for (int i = 0; i < PROF_SLOTS; ++i) { g_prof_ms[i] = 0; g_prof_n[i] = 0; }
+    return P3D_OK;
+}
+
+size_t p3d_render_workspace_bytes(const p3d_render_params* p) {
+    if (!p) return 0;
+    return workspace_layout(p, nullptr, nullptr);
+}
+
+int p3d_render_forward(const p3d_render_params* p, const void* planes, const float* w1, const float* b1, const float* w2,
+                       const float* b2, const float* ray_origins, const float* ray_dirs, const float* u_coarse,
+                       const float* u_fine, void* workspace, size_t workspace_bytes, float* out_rgb, float* out_depth,
+                       float* out_wsum, float* out_xyz, void* stream) {
+    Geom g;
+    int rc = make_geom(p, &g);
+    if (rc) return rc;
+    P3D_REQUIRE(planes && w1 && b1 && w2 && b2 && ray_origins && ray_dirs, "null input pointer");
+    P3D_REQUIRE(out_rgb && out_depth && out_wsum && out_xyz, "null output pointer");
+    P3D_REQUIRE(p->ray_mode == P3D_RAYS_NUMERIC || p->ray_mode == P3D_RAYS_AUTOBOX, "bad ray_mode %d", p->ray_mode);
+    P3D_REQUIRE(!(p->ray_mode == P3D_RAYS_AUTOBOX && p->disparity), "disparity sampling needs numeric ray limits");
+    if ((long long)g.N * g.M == 0) return P3D_OK;
+    Workspace ws;
+    const size_t need = workspace_layout(p, workspace, &ws);
+    if (!workspace || workspace_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return P3D_EWORKSPACE;
+    }
+    if (p->mlp_mode == P3D_MLP_FP32_SIMT)
+        return render_forward_v1(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
+                                 out_depth, out_wsum, out_xyz, (cudaStream_t)stream);
+    set_error("mlp_mode %d has no kernel in this build", p->mlp_mode);
+    return P3D_EUNSUPPORTED;
+}
+
+int p3d_decode_points(const p3d_render_params* p, const void* planes, const float* w1, const float* b1, const float* w2,
+                      const float* b2, const float* coords, int64_t n_points_per_view, float* out_rgb, float* out_sigma,
+                      void* stream) {
+    Geom g;
+    int rc = make_geom(p, &g);
+    if (rc) return rc;
+    P3D_REQUIRE(planes && w1 && b1 && w2 && b2 && coords && out_rgb && out_sigma, "null pointer");
+    P3D_REQUIRE(n_points_per_view >= 0, "negative point count");
+    return decode_points_v1(g, p, planes, w1, b1, w2, b2, coords, n_points_per_view, out_rgb, out_sigma, (cudaStream_t)stream);
+}
+
+int p3d_render_forward_host(const p3d_render_params* p_in, const float* planes_nchw, const float* w1, const float* b1,
+                            const float* w2, const float* b2, const float* cam2world, const float* intrinsics,
+                            int32_t resolution, const float* u_coarse, const float* u_fine, float* out_rgb,
+                            float* out_depth, float* out_wsum, float* out_xyz) {
+    P3D_REQUIRE(p_in && planes_nchw && w1 && b1 && w2 && b2 && cam2world && intrinsics, "null input pointer");
+    P3D_REQUIRE(out_rgb && out_depth && out_wsum && out_xyz, "null output pointer");
+    p3d_render_params p = *p_in;
+    P3D_REQUIRE(p.n_rays == resolution * resolution, "n_rays must equal resolution^2");
+    std::lock_guard<std::mutex> lock(g_arena.mu);
+    if (!g_arena.stream) P3D_CUDA_TRY(cudaStreamCreateWithFlags(&g_arena.stream, cudaStreamNonBlocking));
+    cudaStream_t st = g_arena.stream;
+    const size_t N = p.n_views, M = p.n_rays, C = p.channels, HW = (size_t)p.plane_h * p.plane_w;
+    const size_t plane_elems = N * 3 * C * HW;
+    const size_t esz = p.planes_bf16 ? 2 : 4;
+    p.stride_col = C; p.stride_row = (int64_t)p.plane_w * C; p.stride_plane = (int64_t)HW * C; p.stride_view = 3 * p.stride_plane;
+    void *d_nchw, *d_cl, *d_w, *d_cam, *d_rays, *d_u, *d_out, *d_ws;
+    int rc;
+    if ((rc = g_arena.get(0, plane_elems * 4, &d_nchw))) return rc;
+    if ((rc = g_arena.get(1, plane_elems * esz, &d_cl))) return rc;
+    const size_t nw = (size_t)p.hidden * C + p.hidden + (size_t)p.out_dim * p.hidden + p.out_dim;
+    if ((rc = g_arena.get(2, nw * 4, &d_w))) return rc;
+    if ((rc = g_arena.get(3, N * 25 * 4, &d_cam))) return rc;
+    if ((rc = g_arena.get(4, N * M * 6 * 4, &d_rays))) return rc;
+    const size_t nu = (u_coarse ? N * M * p.n_coarse : 0) + (u_fine ? N * M * p.n_fine : 0);
+    if ((rc = g_arena.get(5, (nu + 1) * 4, &d_u))) return rc;
+    const size_t out_per_ray = (size_t)(p.out_dim - 1) + 1 + 1 + 3;
+    if ((rc = g_arena.get(6, N * M * out_per_ray * 4, &d_out))) return rc;
+    const size_t ws_bytes = p3d_render_workspace_bytes(&p);
+    if ((rc = g_arena.get(7, ws_bytes, &d_ws))) return rc;
+
+    float* dw1 = (float*)d_w; float* db1 = dw1 + (size_t)p.hidden * C; float* dw2 = db1 + p.hidden; float* db2 = dw2 + (size_t)p.out_dim * p.hidden;
+    P3D_CUDA_TRY(cudaMemcpyAsync(d_nchw, planes_nchw, plane_elems * 4, cudaMemcpyHostToDevice, st));
+    P3D_CUDA_TRY(cudaMemcpyAsync(dw1, w1, (size_t)p.hidden * C * 4, cudaMemcpyHostToDevice, st));
+    P3D_CUDA_TRY(cudaMemcpyAsync(db1, b1, (size_t)p.hidden * 4, cudaMemcpyHostToDevice, st));
+    P3D_CUDA_TRY(cudaMemcpyAsync(dw2, w2, (size_t)p.out_dim * p.hidden * 4, cudaMemcpyHostToDevice, st));
+    P3D_CUDA_TRY(cudaMemcpyAsync(db2, b2, (size_t)p.out_dim * 4, cudaMemcpyHostToDevice, st));
+    float* dc2w = (float*)d_cam; float* dK = dc2w + N * 16;
+    P3D_CUDA_TRY(cudaMemcpyAsync(dc2w, cam2world, N * 16 * 4, cudaMemcpyHostToDevice, st));
+    P3D_CUDA_TRY(cudaMemcpyAsync(dK, intrinsics, N * 9 * 4, cudaMemcpyHostToDevice, st));
+    float *duc = nullptr, *duf = nullptr;
+    if (u_coarse) { duc = (float*)d_u; P3D_CUDA_TRY(cudaMemcpyAsync(duc, u_coarse, N * M * p.n_coarse * 4, cudaMemcpyHostToDevice, st)); }
+    if (u_fine) { duf = (float*)d_u + (u_coarse ? N * M * p.n_coarse : 0); P3D_CUDA_TRY(cudaMemcpyAsync(duf, u_fine, N * M * p.n_fine * 4, cudaMemcpyHostToDevice, st)); }
+    if ((rc = p3d_planes_to_channels_last((const float*)d_nchw, d_cl, (int64_t)N * 3, p.channels, p.plane_h, p.plane_w, p.planes_bf16, st))) return rc;
+    float* dro = (float*)d_rays; float* drd = dro + N * M * 3;
+    if ((rc = p3d_raygen_pinhole(dc2w, dK, p.n_views, resolution, dro, drd, st))) return rc;
+    float* drgb = (float*)d_out; float* ddepth = drgb + N * M * (p.out_dim - 1); float* dwsum = ddepth + N * M; float* dxyz = dwsum + N * M;
+    if ((rc = p3d_render_forward(&p, d_cl, dw1, db1, dw2, db2, dro, drd, duc, duf, d_ws, ws_bytes, drgb, ddepth, dwsum, dxyz, st))) return rc;
+    P3D_CUDA_TRY(cudaMemcpyAsync(out_rgb, drgb, N * M * (p.out_dim - 1) * 4, cudaMemcpyDeviceToHost, st));
+    P3D_CUDA_TRY(cudaMemcpyAsync(out_depth, ddepth, N * M * 4, cudaMemcpyDeviceToHost, st));
+    P3D_CUDA_TRY(cudaMemcpyAsync(out_wsum, dwsum, N * M * 4, cudaMemcpyDeviceToHost, st));
+    P3D_CUDA_TRY(cudaMemcpyAsync(out_xyz, dxyz, N * M * 3 * 4, cudaMemcpyDeviceToHost, st));
+    P3D_CUDA_TRY(cudaStreamSynchronize(st));
+    return P3D_OK;
+}
+
+void p3d_host_arena_release(void) {
+    std::lock_guard<std::mutex> lock(g_arena.mu);
+    g_arena.release();
+}
+
+}  // extern "C"

@@ -1,0 +1,216 @@
+"""Drop-in for ``training/volumetric_rendering/renderer.py`` of the reference
+(/root/reference/_train/eg3dc/src/training/volumetric_rendering/renderer.py).
+
+Same names, argument meaning and return shapes as the reference module; the whole of
+``ImportanceRenderer.forward`` (renderer.py:162-264) is one call into the CUDA library
+(``p3d_render_forward``, include/p3d_render.h) instead of ~60 eager PyTorch ops.
+No CPU path: tensors must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional
+
+import torch
+
+from ... import _lib
+from .ray_marcher import MipRayMarcher2
+
+
+def generate_planes(use_triplane: bool = False) -> torch.Tensor:
+    """Axis triplets of the three planes (reference renderer.py:26-50).  Kept for API
+    compatibility (``renderer.plane_axes``); the kernels use the equivalent ``plane_mode``."""
+    third = [[0, 1, 0], [0, 0, 1], [1, 0, 0]] if use_triplane else [[0, 0, 1], [1, 0, 0], [0, 1, 0]]
+    return torch.tensor([[[1, 0, 0], [0, 1, 0], [0, 0, 1]],
+                         [[1, 0, 0], [0, 0, 1], [0, 1, 0]],
+                         third], dtype=torch.float32)
+
+
+def project_onto_planes(planes: torch.Tensor, coordinates: torch.Tensor) -> torch.Tensor:
+    """(n_planes,3,3), (N,M,3) -> (N*n_planes, M, 3).  Reference renderer.py:52-66.
+    Host-side helper only; the CUDA gather selects the two components directly."""
+    N, M, _ = coordinates.shape
+    n_planes = planes.shape[0]
+    inv = torch.linalg.inv(planes)
+    out = torch.einsum('nmc,pcd->npmd', coordinates, inv)
+    return out.reshape(N * n_planes, M, 3)
+
+
+def triplane_crop_mask(xyz_unformatted, thresh, boxwarp, allow_bottom=True):
+    """True where density is forced to -1e3 (reference renderer.py:138-149)."""
+    lim = boxwarp / 2 - thresh
+    return ~((xyz_unformatted[:, :, [0, 2]].abs() <= lim).all(dim=-1, keepdim=True))
+
+
+def cull_clouds_mask(denities, thresh):
+    """Reference renderer.py:150-153."""
+    return (1 - torch.exp(-torch.nn.functional.softplus(denities - 1))) < thresh
+
+
+def _decoder_params(decoder):
+    """Pull the four tensors + gains out of an OSGDecoder-like module (ours or the reference's:
+    triplane.py:516-548 with FullyConnectedLayer, networks_stylegan2.py:101-136)."""
+    fc1, fc2 = decoder.net[0], decoder.net[2]
+    return (fc1.weight, fc1.bias, fc2.weight, fc2.bias,
+            float(fc1.weight_gain), float(fc1.bias_gain), float(fc2.weight_gain), float(fc2.bias_gain),
+            bool(getattr(decoder, 'force_sigmoid', False)))
+
+
+class _PlaneCache:
+    """Channels-last copy of the most recent tri-plane tensor (keyed on storage + version), so the
+    16 views of one subject (generate.py:108-130) pay for the layout pre-pass once."""
+
+    def __init__(self):
+        self.key = None
+        self.buf = None
+
+    def get(self, planes: torch.Tensor, bf16: bool):
+        key = (planes.data_ptr(), planes._version, tuple(planes.shape), tuple(planes.stride()), planes.device, bf16)
+        if key != self.key:
+            N, P, Cc, H, W = planes.shape
+            src = planes if planes.is_contiguous() else planes.contiguous()
+            buf = torch.empty((N, P, H, W, Cc), device=planes.device, dtype=torch.bfloat16 if bf16 else torch.float32)
+            _lib.check(_lib.lib().p3d_planes_to_channels_last(src.data_ptr(), buf.data_ptr(), N * P, Cc, H, W,
+                                                             1 if bf16 else 0, _lib.stream_ptr(planes.device)))
+            self.key, self.buf = key, buf
+        return self.buf
+
+
+class ImportanceRenderer(torch.nn.Module):
+    """Reference: renderer.py:156-387.  Parameter-free, like the reference."""
+
+    def __init__(self, use_triplane: bool = False):
+        super().__init__()
+        self.ray_marcher = MipRayMarcher2()
+        self.use_triplane = bool(use_triplane)
+        self.plane_axes = generate_planes(use_triplane=use_triplane)
+        self.mlp_mode = _lib.P3D_MLP_FP32_SIMT     # decoder arithmetic (see include/p3d_render.h)
+        self.planes_bf16 = False                   # fast-mode plane storage
+        self.injected_noise = None                 # (u_coarse (N,M,S[,1]), u_fine (N*M,Sf)) for parity tests
+        self._planes = _PlaneCache()
+        self._workspace = None
+
+    # ------------------------------------------------------------------ helpers
+    def _params(self, planes_cl, N, M, opts, decoder, triplane_crop, cull_clouds, binarize_clouds):
+        if int(opts.get('triplane_depth', 1)) != 1:
+            raise NotImplementedError('triplane_depth > 1 (multiplane) is outside the accelerated path')
+        if opts.get('density_noise', 0) > 0:
+            raise NotImplementedError('density_noise > 0 is outside the accelerated path')
+        if opts.get('clamp_mode', 'softplus') != 'softplus':
+            raise AssertionError('MipRayMarcher only supports `clamp_mode`=`softplus`!')
+        w1, b1, w2, b2, g1, gb1, g2, gb2, force_sigmoid = _decoder_params(decoder)
+        p = _lib.RenderParams()
+        p.n_views, p.n_rays = N, M
+        p.n_coarse = int(opts.get('depth_resolution', 2))
+        p.n_fine = int(opts.get('depth_resolution_importance', 0) or 0)
+        _, _, H, W, Cc = planes_cl.shape
+        p.channels, p.plane_h, p.plane_w = Cc, H, W
+        p.hidden, p.out_dim = w1.shape[0], w2.shape[0]
+        sv, sp, sr, sc, s1 = planes_cl.stride()
+        assert s1 == 1
+        p.stride_view, p.stride_plane, p.stride_row, p.stride_col = sv, sp, sr, sc
+        p.planes_bf16 = 1 if planes_cl.dtype == torch.bfloat16 else 0
+        p.box_warp = float(opts['box_warp'])
+        rs, re = opts.get('ray_start', 'auto'), opts.get('ray_end', 'auto')
+        if rs == 'auto' and re == 'auto':
+            p.ray_mode = _lib.P3D_RAYS_AUTOBOX
+        else:
+            p.ray_mode, p.ray_start, p.ray_end = _lib.P3D_RAYS_NUMERIC, float(rs), float(re)
+        p.disparity = 1 if opts.get('disparity_space_sampling', False) else 0
+        p.white_back = 1 if opts.get('white_back', False) else 0
+        p.plane_mode = _lib.P3D_PLANES_PANIC3D if self.use_triplane else _lib.P3D_PLANES_EG3D
+        p.triplane_crop = float(triplane_crop or 0)
+        p.cull_clouds = float(cull_clouds or 0)
+        p.binarize_clouds = float(binarize_clouds or 0)
+        p.w1_gain, p.b1_gain, p.w2_gain, p.b2_gain = g1, gb1, g2, gb2
+        p.force_sigmoid = 1 if force_sigmoid else 0
+        p.mlp_mode = int(self.mlp_mode)
+        p.seed = int(torch.empty((), dtype=torch.int64).random_().item()) & 0xFFFFFFFFFFFFFFFF
+        return p, (w1, b1, w2, b2)
+
+    def _planes_cl(self, planes: torch.Tensor) -> torch.Tensor:
+        if planes.dim() != 5 or planes.shape[1] != 3:
+            raise ValueError(f'planes must be (N,3,C,H,W), got {tuple(planes.shape)}')
+        want = torch.bfloat16 if self.planes_bf16 else torch.float32
+        if planes.stride(2) == 1 and planes.dtype == want:
+            return planes.permute(0, 1, 3, 4, 2)            # already channels-last texels: zero-copy view
+        if planes.dtype != torch.float32:
+            planes = planes.float()
+        return self._planes.get(planes, self.planes_bf16)
+
+    @staticmethod
+    def _require_cuda(*tensors):
+        for t in tensors:
+            if t is not None and not t.is_cuda:
+                raise RuntimeError('panic3d_b200.ImportanceRenderer has no CPU path: tensors must be on a CUDA device')
+
+    def _get_workspace(self, nbytes: int, device):
+        ws = self._workspace
+        if ws is None or ws.numel() < nbytes or ws.device != device:
+            self._workspace = ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, planes, decoder, ray_origins, ray_directions, rendering_options,
+                triplane_crop=None, cull_clouds=None, binarize_clouds=None):
+        """-> rgb (N,M,32), depth (N,M,1), weights_sum (N,M,1), xyz (N,M,3).  Reference renderer.py:162-264."""
+        self._require_cuda(planes, ray_origins, ray_directions)
+        if torch.is_grad_enabled() and (planes.requires_grad or any(q.requires_grad for q in decoder.parameters())):
+            raise NotImplementedError('ImportanceRenderer backward is not implemented yet; call under torch.no_grad()')
+        dev = planes.device
+        self.plane_axes = self.plane_axes.to(dev)
+        N, M, _ = ray_origins.shape
+        with torch.cuda.device(dev):
+            planes_cl = self._planes_cl(planes.detach())
+            p, (w1, b1, w2, b2) = self._params(planes_cl, N, M, rendering_options, decoder, triplane_crop, cull_clouds,
+                                               binarize_clouds)
+            ro = ray_origins.detach().float().contiguous()
+            rd = ray_directions.detach().float().contiguous()
+            u_c = u_f = None
+            if self.injected_noise is not None:
+                u_c, u_f = self.injected_noise
+                u_c = u_c.to(dev, torch.float32).contiguous()
+                assert u_c.numel() == N * M * p.n_coarse, 'u_coarse shape'
+                if p.n_fine > 0:
+                    u_f = u_f.to(dev, torch.float32).contiguous()
+                    assert u_f.numel() == N * M * p.n_fine, 'u_fine shape'
+                else:
+                    u_f = None
+            rgb = torch.empty((N, M, p.out_dim - 1), device=dev, dtype=torch.float32)
+            depth = torch.empty((N, M, 1), device=dev, dtype=torch.float32)
+            wsum = torch.empty((N, M, 1), device=dev, dtype=torch.float32)
+            xyz = torch.empty((N, M, 3), device=dev, dtype=torch.float32)
+            L = _lib.lib()
+            nbytes = int(L.p3d_render_workspace_bytes(C.byref(p)))
+            ws = self._get_workspace(nbytes, dev)
+            wt = [t.detach().float().contiguous() for t in (w1, b1, w2, b2)]
+            _lib.check(L.p3d_render_forward(C.byref(p), planes_cl.data_ptr(), wt[0].data_ptr(), wt[1].data_ptr(),
+                                            wt[2].data_ptr(), wt[3].data_ptr(), ro.data_ptr(), rd.data_ptr(),
+                                            _lib.ptr(u_c), _lib.ptr(u_f), ws.data_ptr(), ws.numel(),
+                                            rgb.data_ptr(), depth.data_ptr(), wsum.data_ptr(), xyz.data_ptr(),
+                                            _lib.stream_ptr(dev)))
+        return rgb, depth, wsum, xyz
+
+    # ------------------------------------------------------------------ point queries
+    def run_model(self, planes, decoder, sample_coordinates, sample_directions, options):
+        """-> {'rgb' (N,K,32), 'sigma' (N,K,1), 'xyz'}.  Reference renderer.py:266-280."""
+        self._require_cuda(planes, sample_coordinates)
+        if torch.is_grad_enabled() and (planes.requires_grad or sample_coordinates.requires_grad
+                                        or any(q.requires_grad for q in decoder.parameters())):
+            raise NotImplementedError('run_model backward is not implemented yet; call under torch.no_grad()')
+        dev = planes.device
+        N, K, _ = sample_coordinates.shape
+        with torch.cuda.device(dev):
+            planes_cl = self._planes_cl(planes.detach())
+            opts = dict(options)
+            opts.setdefault('depth_resolution', 2)
+            p, (w1, b1, w2, b2) = self._params(planes_cl, N, 0, opts, decoder, None, None, None)
+            coords = sample_coordinates.detach().float().contiguous()
+            rgb = torch.empty((N, K, p.out_dim - 1), device=dev, dtype=torch.float32)
+            sigma = torch.empty((N, K, 1), device=dev, dtype=torch.float32)
+            wt = [t.detach().float().contiguous() for t in (w1, b1, w2, b2)]
+            _lib.check(_lib.lib().p3d_decode_points(C.byref(p), planes_cl.data_ptr(), wt[0].data_ptr(), wt[1].data_ptr(),
+                                                    wt[2].data_ptr(), wt[3].data_ptr(), coords.data_ptr(), K,
+                                                    rgb.data_ptr(), sigma.data_ptr(), _lib.stream_ptr(dev)))
+        return {'rgb': rgb, 'sigma': sigma, 'xyz': sample_coordinates}
