@@ -33,10 +33,10 @@ FLOP_PER_SAMPLE = 2 * 32 * 64 + 2 * 64 * 33            # 8,320 tensor-eligible F
 BYTES_PER_VIEW = 3 * C * P * P * 4 + R * R * 37 * 4    # tri-plane read once + 37 floats/ray out
 
 
-def workload_config(n_gpus, mlp_mode='fp32_simt'):
+def workload_config(n_gpus, mlp_mode='fp32_simt', planes='fp32'):
     return {'workload': f'{VIEWS} views/GPU x {R}x{R} rays x ({S}+{SF}) samples, {VIEWS} distinct 3x{C}x{P}x{P} fp32 tri-planes/GPU',
             'views_per_gpu': VIEWS, 'rays': R * R, 'samples_coarse': S, 'samples_importance': SF, 'plane': P,
-            'decoder': '32-64-33 softplus', 'mlp_mode': mlp_mode, 'parallelism': f'views sharded x{n_gpus}',
+            'decoder': '32-64-33 softplus', 'mlp_mode': mlp_mode, 'plane_storage': planes, 'parallelism': f'views sharded x{n_gpus}',
             'l2': 'inputs (805 MB planes + 3.4 GB scratch per step) exceed the 126 MB L2; no explicit flush'}
 
 
@@ -102,8 +102,29 @@ def cpu_reference_time(steps, warmup, views=1):
     """Times oracle.render (gather='aten') on `views` view(s) of the bench workload per step."""
     import torch
     from oracle import renderer_oracle as orc
-    torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(0)
+    # torch's CPU ops do not scale to every core of a 100+-core host on tensors this size: probe a
+    # quarter-size render at a few thread counts and give the baseline the fastest one.
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (ncpu, 64, 32, 16, 8) if c <= ncpu}, reverse=True)
+    if len(cands) > 1:
+        pp = torch.randn(1, 3, C, P, P, generator=g)
+        pd = dict(w1=torch.randn(64, C, generator=g), b1=torch.zeros(64), w2=torch.randn(33, 64, generator=g), b2=torch.zeros(33))
+        pc2w, pK = (t[None] for t in orc.camera_params_to_matrix(0.0, 30.0, 1.0, 30.0))
+        pu_c, pu_f = torch.rand(1, 64 * 64, S, 1, generator=g), torch.rand(64 * 64, SF, generator=g)
+        best = (None, 1e30)
+        for c in cands:
+            torch.set_num_threads(c)
+            with torch.no_grad():
+                t0 = time.perf_counter()
+                pro, prd = orc.ray_sampler(pc2w, pK, 64)
+                orc.render(pp, pd, pro, prd, dict(orc.DEFAULT_OPTS), pu_c, pu_f, use_triplane=True, gather='aten')
+                dt = time.perf_counter() - t0
+            if dt < best[1]:
+                best = (c, dt)
+        torch.set_num_threads(best[0])
+    else:
+        torch.set_num_threads(ncpu)
     planes = torch.randn(views, 3, C, P, P, generator=g)
     dec = dict(w1=torch.randn(64, C, generator=g), b1=torch.zeros(64), w2=torch.randn(33, 64, generator=g), b2=torch.zeros(33),
                lr_mul=1.0, force_sigmoid=False)
@@ -176,6 +197,7 @@ def run_ours(args):
     opts = dict(orc.DEFAULT_OPTS)
     renderer, sampler = ImportanceRenderer(use_triplane=True), RaySampler()
     renderer.mlp_mode = mlp_mode
+    renderer.planes_bf16 = args.planes == 'bf16'
     gather_buf = torch.empty((world * VIEWS, R * R, 32), device=dev) if world > 1 else None
 
     def step():
@@ -192,7 +214,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    with torch.no_grad():
+    with torch.no_grad(), ClockSampler(local) as clk:            # nvidia-smi polls through warm-up + timed region
         for _ in range(max(args.warmup, 3)):
             step()
         barrier()
@@ -200,15 +222,15 @@ def run_ours(args):
         L.p3d_profile_read(None, None, 0, 1)
         n0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(local) as clk:
-            barrier()
-            e0.record()
-            for _ in range(args.steps):
-                step()
-            e1.record()
-            barrier()
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
         ms = e0.elapsed_time(e1)
         launches = _lib.launch_count() - n0
+    with torch.no_grad():
         # ---- per-kernel device time for the roofline (separate short run with event brackets enabled)
         L.p3d_profile_enable(1)
         for _ in range(3):
@@ -255,7 +277,7 @@ def run_ours(args):
                                            'layout': slot_ms[3] / 3, 'raygen': slot_ms[4] / 3, 'fused': slot_ms[5] / 3}})
         out = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
                'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-               'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world, args.mlp), 'clocks': clocks,
+               'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world, args.mlp, args.planes), 'clocks': clocks,
                'gpu_launches': int(launches), 'roofline': roof}
         if e2e is not None:
             out['e2e'] = {'value': world * VIEWS * e2e['steps'] / (e2e['ms'] * 1e-3), 'unit': UNIT,
@@ -284,6 +306,7 @@ def run_e2e(L, _lib, planes, decoder, labels, opts, mlp_mode, args, barrier):
     fc1, fc2 = decoder.net[0], decoder.net[2]
     p.w1_gain, p.b1_gain, p.w2_gain, p.b2_gain = float(fc1.weight_gain), float(fc1.bias_gain), float(fc2.weight_gain), float(fc2.bias_gain)
     p.mlp_mode, p.seed = mlp_mode, 7
+    p.planes_bf16 = 1 if args.planes == 'bf16' else 0
     h_planes = planes.cpu().pin_memory()
     h_w = [t.detach().cpu().float().contiguous().pin_memory() for t in (fc1.weight, fc1.bias, fc2.weight, fc2.bias)]
     h_c2w = labels[:, :16].contiguous().pin_memory()
@@ -315,6 +338,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mlp', default=os.environ.get('P3D_BENCH_MLP', 'fp32_simt'), choices=['fp32_simt', 'tc_3xbf16', 'tc_bf16'])
+    ap.add_argument('--planes', default=os.environ.get('P3D_BENCH_PLANES', 'fp32'), choices=['fp32', 'bf16'],
+                    help='storage type of the channels-last tri-plane copy the gather reads (bf16 = fast mode, not parity)')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()

@@ -315,6 +315,9 @@ int p3d_render_forward(const p3d_render_params* p, const void* planes, const flo
     if (p->mlp_mode == P3D_MLP_FP32_SIMT)
         return render_forward_v1(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
                                  out_depth, out_wsum, out_xyz, (cudaStream_t)stream);
+    if (p->mlp_mode == P3D_MLP_TC_3XBF16 || p->mlp_mode == P3D_MLP_TC_BF16)
+        return render_forward_fused(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
+                                    out_depth, out_wsum, out_xyz, (cudaStream_t)stream);
     set_error("mlp_mode %d has no kernel in this build", p->mlp_mode);
     return P3D_EUNSUPPORTED;
 }

@@ -190,3 +190,38 @@ def test_full_size_properties():
     miss = (wsum.squeeze(-1) == 0)
     if miss.any():
         assert (rgb[miss] - 1).abs().max().item() < 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# fused tcgen05 renderer (mlp_mode 1 = 3-pass split bf16 tensor cores, 2 = single-pass bf16)
+# ---------------------------------------------------------------------------------------------
+FUSED_CASES = ['config1', 'mid_train48', 'mid_eval96']
+
+
+@pytest.mark.parametrize('name', FUSED_CASES)
+def test_fused_tc_3xbf16_matches_reference_fixture(name):
+    g = load_golden('render', name)
+    (rgb, depth, wsum, xyz), _ = gpu_render(g['case'], mlp_mode=1)
+    has_cull = bool(g['case'].get('cull_clouds') or g['case'].get('binarize_clouds'))
+    for got, key in ((rgb, 'rgb'), (depth, 'depth'), (wsum, 'wsum'), (xyz, 'xyz')):
+        err = (got - g[key]).abs()
+        if has_cull:
+            assert (err < TOL).float().mean().item() > 0.999, f'{name}:{key}'
+            assert err.max().item() < 2e-2, f'{name}:{key} max {err.max().item()}'
+        else:
+            assert err.max().item() < TOL, f'{name}:{key} max abs err {err.max().item()}'
+        print(f'{name}:{key} fused 3xbf16 max abs err {err.max().item():.3e}')
+
+
+@pytest.mark.parametrize('name', ['config1'])
+def test_fused_tc_bf16_fast_mode_is_close(name):
+    g = load_golden('render', name)
+    (rgb, depth, wsum, xyz), _ = gpu_render(g['case'], mlp_mode=2)
+    assert (rgb - g['rgb']).abs().max().item() < 5e-2
+    assert (rgb - g['rgb']).abs().mean().item() < 5e-3
+    assert (wsum - g['wsum']).abs().max().item() < 5e-2
+
+
+def test_fused_rejects_unsupported_sampling_loudly():
+    with pytest.raises(RuntimeError, match='fused'):
+        gpu_render(RENDER_CASES['small_plain'], mlp_mode=1)       # 12+12 samples: no fused kernel -> error, no fallback
