@@ -59,6 +59,15 @@ struct ProfileScope {
 __device__ __forceinline__ float softplus_t(float x) { return x > 20.f ? x : log1pf(expf(x)); }
 __device__ __forceinline__ float sigmoid_t(float x) { return 1.f / (1.f + expf(-x)); }
 
+// MUFU-based fast math (1 instruction each; ftz).  ex2/lg2: rel/abs error ~2^-22.
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// softplus in base 2: log2(1 + 2^x); equals x beyond the torch threshold (20 nats) to fp32 precision
+__device__ __forceinline__ float softplus2(float x2) { return x2 > 28.853900817779268f ? x2 : lg2_approx(1.f + ex2_approx(x2)); }
+// natural softplus through the base-2 one
+__device__ __forceinline__ float softplus_mufu(float x) { return 0.6931471805599453f * softplus2(1.4426950408889634f * x); }
+
 // Order-preserving float <-> uint mapping for atomicMin/Max on floats of either sign.
 __device__ __forceinline__ unsigned int float_to_ordered(float f) {
     unsigned int u = __float_as_uint(f);

@@ -132,6 +132,8 @@ __device__ __forceinline__ float apply_masks(const Geom& g, float sigma, float x
 //   w_i = alpha_i * prod_{k<i} (1 - alpha_k + 1e-10)
 // t, sg: L sorted samples in shared memory; writes w[0..L-2]; returns (sum w, sum w*t_mid) on all lanes.
 // -------------------------------------------------------------------------------------------
+// FAST: MUFU ex2/lg2 based softplus/exp (abs err ~1e-7) for the fused kernel; false: libm-accurate (v1).
+template <bool FAST = false>
 __device__ __forceinline__ void ray_weights(const float* t, const float* sg, float* w, int L, int lane,
                                             float& wsum, float& dnum) {
     float carry = 1.f, acc_w = 0.f, acc_d = 0.f;
@@ -140,8 +142,9 @@ __device__ __forceinline__ void ray_weights(const float* t, const float* sg, flo
         float alpha = 0.f, factor = 1.f, tmid = 0.f;
         if (i < L - 1) {
             const float delta = t[i + 1] - t[i];
-            const float dens = softplus_t(__fsub_rn(__fmul_rn(__fadd_rn(sg[i], sg[i + 1]), 0.5f), 1.f));
-            alpha = 1.f - expf(-__fmul_rn(dens, delta));
+            const float smid = __fsub_rn(__fmul_rn(__fadd_rn(sg[i], sg[i + 1]), 0.5f), 1.f);
+            if (FAST) alpha = 1.f - ex2_approx(-1.4426950408889634f * __fmul_rn(softplus_mufu(smid), delta));
+            else alpha = 1.f - expf(-__fmul_rn(softplus_t(smid), delta));
             factor = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
             tmid = __fmul_rn(__fadd_rn(t[i], t[i + 1]), 0.5f);
         }
@@ -164,12 +167,13 @@ __device__ __forceinline__ void ray_weights(const float* t, const float* sg, flo
 //   fine    : out, sort_pow2 floats; the first Sf entries are the importance depths, ascending
 //   u_fine  : Sf injected uniforms for this ray (global) or nullptr -> Philox(seed, rng_base + f)
 // -------------------------------------------------------------------------------------------
+template <bool FAST = false>
 __device__ __forceinline__ void importance_ray(const Geom& g, const float* t, const float* sg, float* w, float* cdf,
                                                float* fine, int sort_pow2, const float* u_fine,
                                                unsigned long long rng_base, int lane) {
     const int S = g.S, Sf = g.Sf;
     float wsum, dnum;
-    ray_weights(t, sg, w, S, lane, wsum, dnum);
+    ray_weights<FAST>(t, sg, w, S, lane, wsum, dnum);
     __syncwarp();
     // max_pool1d(k=2,s=1,pad=1) -> avg_pool1d(k=2,s=1) -> +0.01 ; keep [1:-1] ; +eps     (:336-343, :360)
     // pooled[i] = (max(w[i-1],w[i]) + max(w[i],w[i+1]))/2 , i in [1, S-3]
@@ -250,6 +254,7 @@ __device__ __forceinline__ void importance_ray(const Geom& g, const float* t, co
 // On return w[j] holds omega_j = (w_{j-1}+w_j)/2 for merged position j and src[j] names its
 // sample (i < S: coarse i, else fine i-S), so  sum_i w_i (c_i+c_{i+1})/2 == sum_j omega_j c_j.
 // -------------------------------------------------------------------------------------------
+template <bool FAST = false>
 __device__ __forceinline__ void composite_weights(const float* tc, const float* sc, const float* tf, const float* sf,
                                                   int S, int Sf, float* t, float* sg, float* w, int* src, int lane,
                                                   float& wsum, float& dnum) {
@@ -274,7 +279,7 @@ __device__ __forceinline__ void composite_weights(const float* tc, const float* 
         t[pos] = v; sg[pos] = sf[j]; src[pos] = S + j;
     }
     __syncwarp();
-    ray_weights(t, sg, w, L, lane, wsum, dnum);
+    ray_weights<FAST>(t, sg, w, L, lane, wsum, dnum);
     __syncwarp();
     float om[16];                           // up to 512 merged samples per ray
 #pragma unroll

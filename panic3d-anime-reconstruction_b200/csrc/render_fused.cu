@@ -4,18 +4,21 @@
 //   coarse pass (2 MMA tiles of 128 rows: 128 + 64 valid) -> per-ray importance sampling ->
 //   fine pass (2 tiles) -> per-ray merge + alpha/transmittance scan -> weighted colour reduction.
 // Nothing but the final (rgb, depth, wsum, xyz) leaves the SM:
-//   * tri-plane taps: 8 lanes x 16 B = one 128 B texel per tap (same cooperative gather as v1);
-//   * features -> bf16 hi/lo split -> canonical K-major (no-swizzle) UMMA tiles in shared memory;
-//   * layer 1: D1[128x64] (TMEM) = A1[128x32] * W1^T, three tcgen05.mma passes (hi*hi + hi*lo + lo*hi)
-//     per K=16 step = fp32-class accuracy out of bf16 tensor cores (single pass in fast mode);
-//   * epilogue 1: tcgen05.ld D1 -> +b1 -> softplus -> hi/lo split -> A2 tile in shared memory;
-//   * layer 2: D2[t][128x48] (TMEM) = A2[128x64] * W2^T (33 outputs padded to 48);
-//     the logits of all four tiles of the group STAY in TMEM (64 + 4*48 = 256 columns) until the
-//     compositing weights are known, so colours are never stored anywhere;
+//   * taps: each sample's 12 (texel offset, bilinear weight) records are computed ONCE by a lane pair
+//     (32-bit offsets inside the view's tri-plane) and parked in shared memory; the gather proper is
+//     8 lanes x 16 B = one 128 B texel per tap, 12 independent 128-bit loads in flight per lane;
+//   * features -> bf16 hi/lo split (cvt.rn.bf16x2) -> canonical K-major no-swizzle UMMA tiles in smem;
+//   * layer 1: D1[128x64] (TMEM) = A1[128x32] * W1'^T, three tcgen05.mma passes per K=16 step
+//     (hi*hi + hi*lo + lo*hi) = fp32-class accuracy out of bf16 tensor cores (one pass in fast mode);
+//     W1' = W1*gain*log2(e) so the epilogue's softplus is lg2(1 + ex2(.)) - two MUFU ops;
+//   * epilogue 1: tcgen05.ld D1 -> +b1' -> softplus2 -> hi/lo split -> A2 tile in shared memory;
+//   * layer 2: D2[t][128x48] (TMEM) = A2[128x64] * W2'^T; row 0 of W2' (sigma) carries ln2, rows 1..32
+//     are negated so the colour epilogue is rcp(1 + ex2(.)); the logits of all four tiles of the group
+//     STAY in TMEM (64 + 4*48 = 256 columns) until the compositing weights are known;
 //   * sigma (column 0) is read back right away for the importance pass / weights;
 //   * final: tcgen05.ld logits -> sigmoid -> * omega[row] -> warp transpose-reduce -> 32 floats/ray.
-// 256 TMEM columns and ~80 KB of shared memory per CTA => 2 CTAs per SM, which is what overlaps
-// one CTA's gather (L1/L2 bound) with the other's epilogues (issue bound).
+// 256 TMEM columns and ~90 KB of shared memory per CTA => 2 CTAs per SM, which is what overlaps
+// one CTA's gather (L1/L2 latency) with the other's epilogues (issue bound).
 #include "render_device.cuh"
 
 namespace p3d {
@@ -40,12 +43,14 @@ constexpr int kA1Bytes = 128 * 32 * 2;   // 8 KB
 constexpr int kA2Bytes = 128 * 64 * 2;   // 16 KB
 constexpr int kW1Bytes = 64 * 32 * 2;    // 4 KB
 constexpr int kW2Bytes = 48 * 64 * 2;    // 6 KB
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
 struct __align__(1024) FusedSmem {
     unsigned char a1_hi[kA1Bytes], a1_lo[kA1Bytes];
     unsigned char a2_hi[kA2Bytes], a2_lo[kA2Bytes];      // also reused as per-ray scratch between passes
     unsigned char w1_hi[kW1Bytes], w1_lo[kW1Bytes];
     unsigned char w2_hi[kW2Bytes], w2_lo[kW2Bytes];
+    int2 taps[128][12];                                       // per tile row: 12 x (element offset, weight bits)
     float b1[kHidden], b2[kN2];
     float t_c[kRows], sg_c[kRows], t_f[kRows], sg_f[kRows];   // per-row depth / density of both passes
     float om_c[kRows], om_f[kRows];                           // per-row composite weight omega
@@ -66,9 +71,10 @@ struct FusedArgs {
     unsigned int* bounds;
     float *out_rgb, *out_depth, *out_wsum, *out_xyz;
     long long R;              // total rays
-    int n_groups, G;          // ray groups, rays per group
+    int n_groups;
     int single_pass;          // 1: fast mode (bf16 hi*hi only)
-    int sort_pow2;
+    int srow, scol, splane;   // plane strides in elements (32-bit: host checked)
+    float sigma_cull;         // cull/binarize as a threshold on sigma: alpha(sigma) < thr  <=>  sigma < sigma_cull
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -79,14 +85,13 @@ __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t coun
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    const long long t0 = clock64();
-    while (true) {
+    for (int it = 0; it < (1 << 22); ++it) {            // try_wait suspends in hardware; the cap only guards against a hang
         uint32_t ok;
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
         if (ok) return;
-        if (clock64() - t0 > 4000000000ll) { asm volatile("trap;"); }     // ~2 s: never hang the GPU
     }
+    asm volatile("trap;");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -137,49 +142,94 @@ __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
     return __uint_as_float(r);
 }
 
-// ------------------------------------------------------------------------------------------ math
-__device__ __forceinline__ float softplus_fast(float x) { return x > 20.f ? x : __logf(1.f + __expf(x)); }
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-// x = hi + lo (+ 2^-17 x): two bf16 that together carry 16 significant bits
-__device__ __forceinline__ void split_bf16(float x, unsigned short& hi, unsigned short& lo) {
+// ------------------------------------------------------------------------------------------ bf16 split
+// two floats -> packed bf16x2 (element 0 in the low half)
+__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+    return d;
+}
+// (a, b) = hi + lo with hi, lo bf16: 16 significant bits per value
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(a, b);
+    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+__device__ __forceinline__ void split1(float x, unsigned short& hi, unsigned short& lo) {
     const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    const __nv_bfloat16 l = __float2bfloat16_rn(x - __bfloat162float(h));
     hi = __bfloat16_as_ushort(h);
-    lo = __bfloat16_as_ushort(l);
+    lo = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
 }
 // byte offset of element (row, k) inside a canonical K-major tile whose K-cores are `lbo` bytes apart
 __device__ __forceinline__ int tile_off(int row, int k, int lbo) { return (row >> 3) * kSBO + (k >> 3) * lbo + (row & 7) * 16 + (k & 7) * 2; }
 
-// ------------------------------------------------------------------------------------------
+// 4 bilinear taps of one plane as (32-bit element offset, weight); invalid taps -> (0, 0).  renderer.py:68-81
+__device__ __forceinline__ void plane_taps32(const Geom& g, const FusedArgs& a, int pbase, float ca, float cb, int2* out) {
+    const float gx = __fmul_rn(ca, g.coord_scale), gy = __fmul_rn(cb, g.coord_scale);
+    const float fx = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)g.W), 1.f), 0.5f);
+    const float fy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)g.H), 1.f), 0.5f);
+    const bool sane = (fx > -2.f) && (fx < (float)g.W + 1.f) && (fy > -2.f) && (fy < (float)g.H + 1.f);
+    const float x0f = floorf(fx), y0f = floorf(fy);
+    const float wx1 = fx - x0f, wy1 = fy - y0f;
+    const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    const int x0 = sane ? (int)x0f : -4, y0 = sane ? (int)y0f : -4;
+    const bool vx0 = (unsigned)x0 < (unsigned)g.W, vx1 = (unsigned)(x0 + 1) < (unsigned)g.W;
+    const bool vy0 = (unsigned)y0 < (unsigned)g.H, vy1 = (unsigned)(y0 + 1) < (unsigned)g.H;
+    const int o00 = pbase + y0 * a.srow + x0 * a.scol;
+    int4 lo, hi;
+    lo.x = (vx0 && vy0) ? o00 : 0;                     lo.y = __float_as_int((vx0 && vy0) ? wx0 * wy0 : 0.f);
+    lo.z = (vx1 && vy0) ? o00 + a.scol : 0;            lo.w = __float_as_int((vx1 && vy0) ? wx1 * wy0 : 0.f);
+    hi.x = (vx0 && vy1) ? o00 + a.srow : 0;            hi.y = __float_as_int((vx0 && vy1) ? wx0 * wy1 : 0.f);
+    hi.z = (vx1 && vy1) ? o00 + a.srow + a.scol : 0;   hi.w = __float_as_int((vx1 && vy1) ? wx1 * wy1 : 0.f);
+    reinterpret_cast<int4*>(out)[0] = lo;
+    reinterpret_cast<int4*>(out)[1] = hi;
+}
+
 template <bool BF16>
+__device__ __forceinline__ float4 load_quad32(const void* vbase, int off) {
+    if (BF16) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(vbase) + off));
+        return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
+                           __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+    } else {
+        return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(vbase) + off));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <bool BF16, int S>
 __global__ void __launch_bounds__(kThreads, 2) k_render_fused(const FusedArgs a) {
+    constexpr int Sf = S;
+    constexpr int G = kRows / S;
+    constexpr int SORT_P2 = S <= 64 ? 64 : 128;
     extern __shared__ unsigned char smem_raw[];
     FusedSmem& sm = *reinterpret_cast<FusedSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const Geom& g = a.g;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int S = g.S, Sf = g.Sf, G = a.G;
 
-    // ---------------- one-time setup: TMEM, barrier, decoder weights as UMMA B tiles
+    // ---------------- one-time setup: TMEM, barrier, decoder weights as UMMA B tiles (scalings folded in)
     if (warp == 0) tmem_alloc(&sm.tmem_base, kTmemCols);
     if (tid == 32) { mbar_init(&sm.mbar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    for (int i = tid; i < kHidden * kC; i += kThreads) {            // W1 (64,32): row n = i/32, k = i%32
+    for (int i = tid; i < kHidden * kC; i += kThreads) {            // W1' = W1 * gain * log2(e)
         const int n = i / kC, k = i % kC;
         unsigned short hi, lo;
-        split_bf16(__fmul_rn(a.w1[i], g.w1_gain), hi, lo);
+        split1(__fmul_rn(a.w1[i], g.w1_gain) * kLog2e, hi, lo);
         const int off = tile_off(n, k, kLBO_W1);
         *reinterpret_cast<unsigned short*>(sm.w1_hi + off) = hi;
         *reinterpret_cast<unsigned short*>(sm.w1_lo + off) = lo;
     }
-    for (int i = tid; i < kN2 * kHidden; i += kThreads) {           // W2 (33,64) zero-padded to 48 rows
+    for (int i = tid; i < kN2 * kHidden; i += kThreads) {           // W2' : row 0 * ln2 ; rows 1..32 negated ; rows 33..47 zero
         const int n = i / kHidden, k = i % kHidden;
         unsigned short hi = 0, lo = 0;
-        if (n < kOut) split_bf16(__fmul_rn(a.w2[n * kHidden + k], g.w2_gain), hi, lo);
+        if (n < kOut) {
+            const float w = __fmul_rn(a.w2[n * kHidden + k], g.w2_gain);
+            split1(n == 0 ? w * kLn2 : -w, hi, lo);
+        }
         const int off = tile_off(n, k, kLBO_W2);
         *reinterpret_cast<unsigned short*>(sm.w2_hi + off) = hi;
         *reinterpret_cast<unsigned short*>(sm.w2_lo + off) = lo;
     }
-    if (tid < kHidden) sm.b1[tid] = __fmul_rn(a.b1[tid], g.b1_gain);
-    if (tid < kN2) sm.b2[tid] = tid < kOut ? __fmul_rn(a.b2[tid], g.b2_gain) : 0.f;
+    if (tid < kHidden) sm.b1[tid] = __fmul_rn(a.b1[tid], g.b1_gain) * kLog2e;
+    if (tid < kN2) sm.b2[tid] = tid == 0 ? __fmul_rn(a.b2[0], g.b2_gain) : (tid < kOut ? -__fmul_rn(a.b2[tid], g.b2_gain) * kLog2e : 0.f);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -197,55 +247,105 @@ __global__ void __launch_bounds__(kThreads, 2) k_render_fused(const FusedArgs a)
 
     for (int grp = blockIdx.x; grp < a.n_groups; grp += gridDim.x) {
         const long long ray0 = (long long)grp * G;
+        const int view = (int)(ray0 / g.M);                          // a group never straddles views (M % G == 0)
+        const void* vplanes = BF16 ? (const void*)(reinterpret_cast<const __nv_bfloat16*>(a.planes) + (long long)view * g.stride_view)
+                                   : (const void*)(reinterpret_cast<const float*>(a.planes) + (long long)view * g.stride_view);
 
         // =================================================================== two passes x two tiles
+#pragma unroll 1
         for (int pass = 0; pass < 2; ++pass) {
-            const int per_ray = pass == 0 ? S : Sf;
             float* t_arr = pass == 0 ? sm.t_c : sm.t_f;
             float* sg_arr = pass == 0 ? sm.sg_c : sm.sg_f;
+#pragma unroll 1
             for (int tile = 0; tile < 2; ++tile) {
                 const int rows_valid = tile == 0 ? 128 : kRows - 128;
-                // ------------------------------------------------ gather: 16 rows per warp, 4 per round
-                {
-                    const int sub = lane >> 3, q = lane & 7;
-#pragma unroll 1
-                    for (int round = 0; round < 4; ++round) {
-                        const int trow = warp * 16 + round * 4 + sub;      // row inside the tile
-                        if (trow >= rows_valid) continue;                  // warp-uniform (16-row granularity)
-                        const int prow = tile * 128 + trow;                // row inside the pass
-                        const int rl = prow / per_ray, s = prow - rl * per_ray;
+                const bool warp_live = warp * 16 < rows_valid;           // 16 rows per warp
+                if (warp_live) {
+                    // -------------------------------------------- A) taps: one lane pair per row
+                    {
+                        const int trow = warp * 16 + (lane >> 1), half = lane & 1;
+                        const int prow = tile * 128 + trow;
+                        const int rl = prow / S, s = prow - rl * S;
                         const long long ray = ray0 + rl;
-                        float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-                        float px = 0.f, pz = 0.f, tval = 0.f;
-                        if (ray < a.R) {
-                            if (pass == 0) {
+                        const bool live = ray < a.R;
+                        float tval = 0.f;
+                        if (pass == 0) {
+                            float u = 0.f;
+                            if (half == 0 && live) {
                                 const long long gidx = ray * S + s;
-                                const float u = a.u_c ? a.u_c[gidx] : philox_uniform(g.seed, (uint64_t)gidx, 0u);
-                                float t0 = 0.f, t1 = 0.f;
-                                if (g.ray_mode == P3D_RAYS_AUTOBOX) {
-                                    t0 = a.ray_t0[ray]; t1 = a.ray_t1[ray];
-                                    if (!(t1 > t0) && a.bounds[4]) { t0 = ordered_to_float(a.bounds[2]); t1 = ordered_to_float(a.bounds[3]); }
-                                }
-                                tval = coarse_depth(g, s, u, t0, t1);
-                            } else {
-                                tval = t_arr[prow];
+                                u = a.u_c ? a.u_c[gidx] : philox_uniform(g.seed, (uint64_t)gidx, 0u);
                             }
+                            u = __shfl_sync(0xffffffffu, u, lane & ~1);
+                            float t0 = 0.f, t1 = 0.f;
+                            if (g.ray_mode == P3D_RAYS_AUTOBOX && live) {
+                                t0 = a.ray_t0[ray]; t1 = a.ray_t1[ray];
+                                if (!(t1 > t0) && a.bounds[4]) { t0 = ordered_to_float(a.bounds[2]); t1 = ordered_to_float(a.bounds[3]); }
+                            }
+                            tval = coarse_depth(g, s, u, t0, t1);
+                        } else {
+                            tval = t_arr[prow];
+                        }
+                        float px = 0.f, py = 0.f, pz = 0.f;
+                        if (live) {
                             const float* o = a.ro + ray * 3;
                             const float* d = a.rd + ray * 3;
                             px = __fadd_rn(o[0], __fmul_rn(tval, d[0]));
-                            const float py = __fadd_rn(o[1], __fmul_rn(tval, d[1]));
+                            py = __fadd_rn(o[1], __fmul_rn(tval, d[1]));
                             pz = __fadd_rn(o[2], __fmul_rn(tval, d[2]));
-                            const int view = (int)(ray / g.M);
-                            f = gather_features<BF16>(a.planes, g, view, px, py, pz, q);
+                        } else {
+                            px = py = pz = 1e30f;                         // all taps invalid -> zero features
                         }
-                        unsigned short h0, h1, h2, h3, l0, l1, l2, l3;
-                        split_bf16(f.x, h0, l0); split_bf16(f.y, h1, l1); split_bf16(f.z, h2, l2); split_bf16(f.w, h3, l3);
-                        const int off = tile_off(trow, 4 * q, kLBO_A);
-                        *reinterpret_cast<uint2*>(sm.a1_hi + off) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
-                        *reinterpret_cast<uint2*>(sm.a1_lo + off) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
-                        if (q == 0) {
+                        int2* tp = sm.taps[trow];
+                        if (half == 0) {
+                            plane_taps32(g, a, 0, px, py, tp);
+                            plane_taps32(g, a, a.splane, px, pz, tp + 4);
+                        } else {
+                            const bool pm = g.plane_mode == P3D_PLANES_PANIC3D;
+                            plane_taps32(g, a, 2 * a.splane, pm ? py : pz, pm ? pz : px, tp + 8);
                             if (pass == 0) t_arr[prow] = tval;
                             sm.xz[prow * 2] = px; sm.xz[prow * 2 + 1] = pz;
+                        }
+                    }
+                    __syncwarp();
+                    // -------------------------------------------- B) gather: 4 rows per round, 8 lanes per row
+                    {
+                        const int sub = lane >> 3, q = lane & 7;
+#pragma unroll 1
+                        for (int round = 0; round < 4; ++round) {
+                            const int trow = warp * 16 + round * 4 + sub;
+                            const int4* tp = reinterpret_cast<const int4*>(sm.taps[trow]);
+                            int4 tk[6];
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) tk[k] = tp[k];
+                            float4 v[12];
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) {
+                                v[2 * k] = load_quad32<BF16>(vplanes, tk[k].x + 4 * q);
+                                v[2 * k + 1] = load_quad32<BF16>(vplanes, tk[k].z + 4 * q);
+                            }
+                            float4 f[3];
+#pragma unroll
+                            for (int p = 0; p < 3; ++p) {
+                                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                                for (int k = 0; k < 2; ++k) {
+                                    const int4 t2 = tk[2 * p + k];
+                                    const float wa = __int_as_float(t2.y), wb = __int_as_float(t2.w);
+                                    const float4 va = v[4 * p + 2 * k], vb = v[4 * p + 2 * k + 1];
+                                    acc.x = fmaf(va.x, wa, acc.x); acc.y = fmaf(va.y, wa, acc.y); acc.z = fmaf(va.z, wa, acc.z); acc.w = fmaf(va.w, wa, acc.w);
+                                    acc.x = fmaf(vb.x, wb, acc.x); acc.y = fmaf(vb.y, wb, acc.y); acc.z = fmaf(vb.z, wb, acc.z); acc.w = fmaf(vb.w, wb, acc.w);
+                                }
+                                f[p] = acc;
+                            }
+                            const float third = 1.f / 3.f;               // mean over planes (x 1/3: within 1 ulp of the divide)
+                            const float fx = ((f[0].x + f[1].x) + f[2].x) * third, fy = ((f[0].y + f[1].y) + f[2].y) * third;
+                            const float fz = ((f[0].z + f[1].z) + f[2].z) * third, fw = ((f[0].w + f[1].w) + f[2].w) * third;
+                            uint32_t h01, l01, h23, l23;
+                            split2(fx, fy, h01, l01);
+                            split2(fz, fw, h23, l23);
+                            const int off = tile_off(trow, 4 * q, kLBO_A);
+                            *reinterpret_cast<uint2*>(sm.a1_hi + off) = make_uint2(h01, h23);
+                            *reinterpret_cast<uint2*>(sm.a1_lo + off) = make_uint2(l01, l23);
                         }
                     }
                 }
@@ -268,29 +368,23 @@ __global__ void __launch_bounds__(kThreads, 2) k_render_fused(const FusedArgs a)
                 }
                 mbar_wait(&sm.mbar, phase); phase ^= 1;
                 tc_fence_after();
-                // ------------------------------------------------ epilogue 1: softplus -> A2 (hi/lo)
-                {
+                // ------------------------------------------------ epilogue 1: softplus2 -> A2 (hi/lo)
+                if ((warp & 3) * 32 < rows_valid) {                    // warp-uniform
                     const int trow = (warp & 3) * 32 + lane;
                     const int chunk = warp >> 2;                           // columns [32*chunk, 32*chunk+32)
-                    if ((warp & 3) * 32 < rows_valid) {                    // warp-uniform
-                        float v[32];
-                        tmem_ld32(tmem + lane_base + 32 * chunk, v);
+                    float v[32];
+                    tmem_ld32(tmem + lane_base + 32 * chunk, v);
 #pragma unroll
-                        for (int c8 = 0; c8 < 4; ++c8) {
-                            uint32_t ph[4], pl[4];
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        uint32_t ph[4], pl[4];
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const int j = c8 * 8 + 2 * e;
-                                unsigned short h0, l0, h1, l1;
-                                split_bf16(softplus_fast(v[j] + sm.b1[32 * chunk + j]), h0, l0);
-                                split_bf16(softplus_fast(v[j + 1] + sm.b1[32 * chunk + j + 1]), h1, l1);
-                                ph[e] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                                pl[e] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-                            }
-                            const int off = tile_off(trow, 32 * chunk + 8 * c8, kLBO_A);
-                            *reinterpret_cast<uint4*>(sm.a2_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                            *reinterpret_cast<uint4*>(sm.a2_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = c8 * 8 + 2 * e;
+                            split2(softplus2(v[j] + sm.b1[32 * chunk + j]), softplus2(v[j + 1] + sm.b1[32 * chunk + j + 1]), ph[e], pl[e]);
                         }
+                        const int off = tile_off(trow, 32 * chunk + 8 * c8, kLBO_A);
+                        *reinterpret_cast<uint4*>(sm.a2_hi + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        *reinterpret_cast<uint4*>(sm.a2_lo + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
                     }
                 }
                 fence_proxy_async();
@@ -313,11 +407,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_render_fused(const FusedArgs a)
                 }
                 mbar_wait(&sm.mbar, phase); phase ^= 1;
                 tc_fence_after();
-                // ------------------------------------------------ sigma = column 0 (+ masks)
+                // ------------------------------------------------ sigma = column 0 (+ crop / cull masks as thresholds)
                 if (warp < 4 && warp * 32 < rows_valid) {
                     const int prow = tile * 128 + warp * 32 + lane;
-                    const float sraw = tmem_ld1(d2 + lane_base) + sm.b2[0];
-                    sg_arr[prow] = apply_masks(g, sraw, sm.xz[prow * 2], sm.xz[prow * 2 + 1]);
+                    float sg = tmem_ld1(d2 + lane_base) + sm.b2[0];
+                    if (g.crop_on && !((fabsf(sm.xz[prow * 2]) <= g.crop_limit) && (fabsf(sm.xz[prow * 2 + 1]) <= g.crop_limit))) sg = -1e3f;
+                    if (g.binarize_on) sg = sg < a.sigma_cull ? -1e3f : 1e3f;
+                    else if (g.cull_on && sg < a.sigma_cull) sg = -1e3f;
+                    sg_arr[prow] = sg;
                 }
                 tc_fence_before();
                 __syncthreads();
@@ -325,17 +422,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_render_fused(const FusedArgs a)
 
             if (pass == 0) {
                 // -------------------------------------------- importance sampling, one warp per ray
-                if (Sf > 0) {
-                    for (int rl = warp; rl < G; rl += kWarps) {
-                        const long long ray = ray0 + rl;
-                        float* wv = scratch + rl * (2 * S + a.sort_pow2);
-                        float* cdf = wv + S;
-                        float* fine = cdf + S;
-                        if (ray < a.R) {
-                            importance_ray(g, sm.t_c + rl * S, sm.sg_c + rl * S, wv, cdf, fine, a.sort_pow2,
-                                           a.u_f ? a.u_f + ray * Sf : nullptr, (unsigned long long)(ray * Sf), lane);
-                            for (int f = lane; f < Sf; f += 32) sm.t_f[rl * Sf + f] = fine[f];
-                        }
+                for (int rl = warp; rl < G; rl += kWarps) {
+                    const long long ray = ray0 + rl;
+                    float* wv = scratch + rl * (2 * S + SORT_P2);
+                    float* cdf = wv + S;
+                    float* fine = cdf + S;
+                    if (ray < a.R) {
+                        importance_ray<true>(g, sm.t_c + rl * S, sm.sg_c + rl * S, wv, cdf, fine, SORT_P2,
+                                             a.u_f ? a.u_f + ray * Sf : nullptr, (unsigned long long)(ray * Sf), lane);
+                        for (int f = lane; f < Sf; f += 32) sm.t_f[rl * Sf + f] = fine[f];
                     }
                 }
                 __syncthreads();
@@ -347,13 +442,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_render_fused(const FusedArgs a)
         for (int rl = warp; rl < G; rl += kWarps) {
             const long long ray = ray0 + rl;
             if (ray >= a.R) continue;
-            const int L = S + Sf;
+            constexpr int L = S + Sf;
             float* t = scratch + rl * 4 * L;
             float* sg = t + L;
             float* w = sg + L;
             int* src = reinterpret_cast<int*>(w + L);
             float wsum, dnum;
-            composite_weights(sm.t_c + rl * S, sm.sg_c + rl * S, sm.t_f + rl * Sf, sm.sg_f + rl * Sf, S, Sf, t, sg, w, src, lane, wsum, dnum);
+            composite_weights<true>(sm.t_c + rl * S, sm.sg_c + rl * S, sm.t_f + rl * Sf, sm.sg_f + rl * Sf, S, Sf, t, sg, w, src, lane, wsum, dnum);
             for (int j = lane; j < L; j += 32) {
                 const int s = src[j];
                 if (s < S) sm.om_c[rl * S + s] = w[j]; else sm.om_f[rl * Sf + (s - S)] = w[j];
@@ -376,33 +471,29 @@ __global__ void __launch_bounds__(kThreads, 2) k_render_fused(const FusedArgs a)
         tc_fence_after();
         for (int tt = warp >> 2; tt < 4; tt += 2) {                  // warps 0-3: tiles 0,2   warps 4-7: tiles 1,3
             const int pass = tt >> 1, tile = tt & 1;
-            if (pass == 1 && Sf == 0) continue;
             const int rows_valid = tile == 0 ? 128 : kRows - 128;
             if ((warp & 3) * 32 >= rows_valid) continue;
-            const int per_ray = pass == 0 ? S : Sf;
             const int prow = tile * 128 + (warp & 3) * 32 + lane;
-            const int rl = prow / per_ray;
+            const int rl = prow / S;
             const bool live = ray0 + rl < a.R;
             const float om = live ? (pass == 0 ? sm.om_c[prow] : sm.om_f[prow]) : 0.f;
+            const float ca = g.force_sigmoid ? om : 1.002f * om, cb = g.force_sigmoid ? 0.f : -0.001f * om;
             float v[32];
             tmem_ld32(tmem + 64 + kN2 * tt + 1 + lane_base, v);
 #pragma unroll
-            for (int c = 0; c < kRgb; ++c) {
-                float col = sigmoid_fast(v[c] + sm.b2[1 + c]);
-                if (!g.force_sigmoid) col = fmaf(col, 1.002f, -0.001f);
-                v[c] = om * col;
-            }
-            // rows of one warp belong to at most two rays (per_ray >= 32): reduce each separately
+            for (int c = 0; c < kRgb; ++c)                           // omega * (sigmoid(o) [*1.002 - 0.001]),  z = -o*log2(e)
+                v[c] = fmaf(rcp_approx(1.f + ex2_approx(v[c] + sm.b2[1 + c])), ca, cb);
+            // rows of one warp belong to at most two rays (S >= 32): reduce each separately
             const int rl_lo = __shfl_sync(0xffffffffu, rl, 0), rl_hi = __shfl_sync(0xffffffffu, rl, 31);
             for (int target = rl_lo; target <= rl_hi; ++target) {
                 float r[32];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) r[c] = rl == target ? v[c] : 0.f;
+                for (int c = 0; c < 32; ++c) r[c] = (S % 32 == 0 || rl == target) ? v[c] : 0.f;
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) {
+                    const bool up = (lane & off) != 0;
 #pragma unroll
                     for (int i = 0; i < off; ++i) {
-                        const bool up = (lane & off) != 0;
                         const float send = up ? r[i] : r[i + off];
                         const float keep = up ? r[i + off] : r[i];
                         r[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
@@ -434,7 +525,10 @@ int launch_ray_limits(const float* ro, const float* rd, long long R, float h, fl
 int launch_depth_finalize(float* depth, long long R, const unsigned int* bounds, cudaStream_t stream);
 
 bool fused_supported(const Geom& g) {
-    return (g.S == 96 || g.S == 48) && (g.Sf == g.S) && ((long long)g.M % (kRows / g.S) == 0);
+    if (!((g.S == 96 || g.S == 48) && (g.Sf == g.S) && ((long long)g.M % (kRows / g.S) == 0))) return false;
+    // 32-bit tap offsets inside one view's tri-plane
+    const long long span = 2 * g.stride_plane + (long long)(g.H - 1) * g.stride_row + (long long)(g.W - 1) * g.stride_col + kC;
+    return g.stride_plane >= 0 && g.stride_row >= 0 && g.stride_col >= 0 && span < (1ll << 31);
 }
 
 int render_forward_fused(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
@@ -442,7 +536,8 @@ int render_forward_fused(const Geom& g, const p3d_render_params* p, const void* 
                          const float* u_f, const Workspace& ws, float* out_rgb, float* out_depth, float* out_wsum,
                          float* out_xyz, cudaStream_t stream) {
     if (!fused_supported(g)) {
-        set_error("fused tcgen05 renderer supports depth_resolution == depth_resolution_importance in {48, 96} (got %d, %d)", g.S, g.Sf);
+        set_error("fused tcgen05 renderer supports depth_resolution == depth_resolution_importance in {48, 96} (got %d, %d) "
+                  "with non-negative plane strides below 2^31 elements per view", g.S, g.Sf);
         return P3D_EUNSUPPORTED;
     }
     const long long R = (long long)g.N * g.M;
@@ -454,10 +549,15 @@ int render_forward_fused(const Geom& g, const p3d_render_params* p, const void* 
     a.g = g; a.planes = planes; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.ro = ro; a.rd = rd; a.u_c = u_c; a.u_f = u_f;
     a.ray_t0 = ws.ray_t0; a.ray_t1 = ws.ray_t1; a.bounds = ws.bounds;
     a.out_rgb = out_rgb; a.out_depth = out_depth; a.out_wsum = out_wsum; a.out_xyz = out_xyz;
-    a.R = R; a.G = kRows / g.S; a.n_groups = (int)((R + a.G - 1) / a.G);
+    const int G = kRows / g.S;
+    a.R = R; a.n_groups = (int)((R + G - 1) / G);
     a.single_pass = p->mlp_mode == P3D_MLP_TC_BF16;
-    int p2 = 1; while (p2 < g.Sf) p2 <<= 1;
-    a.sort_pow2 = p2;
+    a.srow = (int)g.stride_row; a.scol = (int)g.stride_col; a.splane = (int)g.stride_plane;
+    // alpha(sigma) = 1 - exp(-softplus(sigma - 1)) < thr   <=>   sigma < 1 + log(expm1(-log1p(-thr)))   (monotone)
+    if (g.cull_on || g.binarize_on) {
+        const double thr = (double)g.cull_thresh;
+        a.sigma_cull = thr >= 1.0 ? INFINITY : (thr <= 0.0 ? -INFINITY : (float)(1.0 + log(expm1(-log1p(-thr)))));
+    }
     static int n_sm = 0;
     if (!n_sm) {
         int dev = 0;
@@ -465,7 +565,9 @@ int render_forward_fused(const Geom& g, const p3d_render_params* p, const void* 
         P3D_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
     const size_t smem = sizeof(FusedSmem) + 1024;
-    auto kern = p->planes_bf16 ? k_render_fused<true> : k_render_fused<false>;
+    void (*kern)(FusedArgs) = nullptr;
+    if (g.S == 96) kern = p->planes_bf16 ? k_render_fused<true, 96> : k_render_fused<false, 96>;
+    else kern = p->planes_bf16 ? k_render_fused<true, 48> : k_render_fused<false, 48>;
     P3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = a.n_groups < 2 * n_sm ? a.n_groups : 2 * n_sm;
     {

@@ -1,0 +1,56 @@
+"""CPU: the drop-in mechanism.  With the reference tree present (build container only) the reference's own
+TriPlaneGenerator must pick up this package's renderer / ray sampler by import name, unchanged."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = '/root/reference'
+
+
+def test_install_registers_modules():
+    code = textwrap.dedent('''
+        import sys
+        sys.path.insert(0, %r)
+        import panic3d_b200.dropin as d
+        names = d.install()
+        assert 'training.volumetric_rendering.renderer' in names, names
+        import panic3d_b200.training.volumetric_rendering.renderer as ours
+        assert sys.modules['training.volumetric_rendering.renderer'] is ours
+        print('ok')
+    ''' % ROOT)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree only exists in the build container')
+def test_reference_generator_uses_dropin_modules():
+    code = textwrap.dedent('''
+        import os, sys, types
+        os.environ['PROJECT_DN'] = %(ref)r
+        sys.path[:0] = [%(root)r, %(ref)r, %(ref)r + '/_train/eg3dc/src']
+        sys.modules['kornia'] = types.ModuleType('kornia')
+        import panic3d_b200.dropin as d
+        d.install(ops=False)
+        import training.triplane as tp                       # the reference's own file
+        assert tp.__file__.startswith(%(ref)r)
+        import panic3d_b200.training.volumetric_rendering.renderer as ours_r
+        import panic3d_b200.training.volumetric_rendering.ray_sampler as ours_s
+        assert tp.ImportanceRenderer is ours_r.ImportanceRenderer
+        assert tp.RaySampler is ours_s.RaySampler
+        rk = dict(superresolution_module='training.superresolution.SuperresolutionHybrid8XDC', sr_antialias=True,
+                  use_triplane=True, c_gen_conditioning_zero=True, decoder_lr_mul=1, box_warp=0.7)
+        G = tp.TriPlaneGenerator(z_dim=64, c_dim=25, w_dim=64, img_resolution=512, img_channels=3, rendering_kwargs=rk,
+                                 cond_mode='none', mapping_kwargs=dict(num_layers=1), channel_base=2048, channel_max=32,
+                                 sr_kwargs=dict(channel_base=2048, channel_max=32, fused_modconv_default='inference_only'))
+        assert type(G.renderer) is ours_r.ImportanceRenderer and G.renderer.use_triplane
+        assert type(G.ray_sampler) is ours_s.RaySampler
+        assert sum(p.numel() for p in G.renderer.parameters()) == 0
+        assert tuple(G.decoder.net[0].weight.shape) == (64, 32) and tuple(G.decoder.net[2].weight.shape) == (33, 64)
+        print('ok')
+    ''' % dict(root=ROOT, ref=REF))
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+    assert r.returncode == 0 and 'ok' in r.stdout, (r.stdout[-1000:], r.stderr[-3000:])
