@@ -310,6 +310,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_render_fused(const FusedArgs a)
                     // -------------------------------------------- B) gather: 4 rows per round, 8 lanes per row
                     {
                         const int sub = lane >> 3, q = lane & 7;
+                        const void* qplanes = BF16 ? (const void*)(reinterpret_cast<const __nv_bfloat16*>(vplanes) + 4 * q)
+                                                   : (const void*)(reinterpret_cast<const float*>(vplanes) + 4 * q);
 #pragma unroll 1
                         for (int round = 0; round < 4; ++round) {
                             const int trow = warp * 16 + round * 4 + sub;
@@ -320,8 +322,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_render_fused(const FusedArgs a)
                             float4 v[12];
 #pragma unroll
                             for (int k = 0; k < 6; ++k) {
-                                v[2 * k] = load_quad32<BF16>(vplanes, tk[k].x + 4 * q);
-                                v[2 * k + 1] = load_quad32<BF16>(vplanes, tk[k].z + 4 * q);
+                                v[2 * k] = load_quad32<BF16>(qplanes, tk[k].x);
+                                v[2 * k + 1] = load_quad32<BF16>(qplanes, tk[k].z);
                             }
                             float4 f[3];
 #pragma unroll
@@ -421,38 +423,171 @@ __global__ void __launch_bounds__(kThreads, 2) k_render_fused(const FusedArgs a)
             }  // tile
 
             if (pass == 0) {
-                // -------------------------------------------- importance sampling, one warp per ray
-                for (int rl = warp; rl < G; rl += kWarps) {
-                    const long long ray = ray0 + rl;
-                    float* wv = scratch + rl * (2 * S + SORT_P2);
-                    float* cdf = wv + S;
-                    float* fine = cdf + S;
-                    if (ray < a.R) {
-                        importance_ray<true>(g, sm.t_c + rl * S, sm.sg_c + rl * S, wv, cdf, fine, SORT_P2,
-                                             a.u_f ? a.u_f + ray * Sf : nullptr, (unsigned long long)(ray * Sf), lane);
-                        for (int f = lane; f < Sf; f += 32) sm.t_f[rl * Sf + f] = fine[f];
+                // -------------------------------------------- importance sampling (renderer.py:328-387), whole CTA:
+                //   (1) thread/interval: alpha   (2) warp/ray: transmittance scan -> weights -> pooled pdf -> cdf
+                //   (3) thread/fine sample: inverse CDF   (4) thread/fine sample: rank sort -> ascending t_f
+                float* i_alpha = scratch;              // [192]
+                float* i_fac = scratch + 192;          // [192]
+                float* i_w = scratch + 384;            // [192]
+                float* i_cdf = scratch + 576;          // [192]
+                float* i_tfu = scratch + 768;          // [192] unsorted importance depths
+                if (tid < kRows) {
+                    const int rl = tid / S, i = tid - rl * S;
+                    float alpha = 0.f, fac = 1.f;
+                    if (i < S - 1) {
+                        const float smid = __fsub_rn(__fmul_rn(__fadd_rn(sm.sg_c[tid], sm.sg_c[tid + 1]), 0.5f), 1.f);
+                        alpha = 1.f - ex2_approx(-kLog2e * __fmul_rn(softplus_mufu(smid), sm.t_c[tid + 1] - sm.t_c[tid]));
+                        fac = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
                     }
+                    i_alpha[tid] = alpha; i_fac[tid] = fac;
+                }
+                __syncthreads();
+                if (warp < G) {
+                    const int rl = warp, nb = S - 3;
+                    float carry = 1.f;
+#pragma unroll
+                    for (int c = 0; c < (S + 31) / 32; ++c) {
+                        const int i = c * 32 + lane;
+                        const float f = i < S - 1 ? i_fac[rl * S + i] : 1.f;
+                        const float incl = warp_scan_mul(f, lane);
+                        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                        if (lane == 0) excl = 1.f;
+                        if (i < S - 1) i_w[rl * S + i] = i_alpha[rl * S + i] * (carry * excl);
+                        carry *= __shfl_sync(0xffffffffu, incl, 31);
+                    }
+                    __syncwarp();
+                    float my[(S + 31) / 32];
+                    float part = 0.f;
+#pragma unroll
+                    for (int c = 0; c < (S + 31) / 32; ++c) {
+                        const int k = c * 32 + lane;
+                        float v = 0.f;
+                        if (k < nb) {
+                            const float* w = i_w + rl * S + k;          // pooled[i = k+1]
+                            v = __fadd_rn(__fadd_rn(__fmul_rn(__fadd_rn(fmaxf(w[0], w[1]), fmaxf(w[1], w[2])), 0.5f), 0.01f), 1e-5f);
+                        }
+                        my[c] = v; part += v;
+                    }
+                    const float total = warp_sum(part);
+                    float csum = 0.f;
+#pragma unroll
+                    for (int c = 0; c < (S + 31) / 32; ++c) {
+                        const int k = c * 32 + lane;
+                        const float incl = warp_scan_add(k < nb ? __fdiv_rn(my[c], total) : 0.f, lane) + csum;
+                        if (k < nb) i_cdf[rl * S + k + 1] = incl;
+                        csum = __shfl_sync(0xffffffffu, incl, 31);
+                    }
+                    if (lane == 0) i_cdf[rl * S] = 0.f;
+                }
+                __syncthreads();
+                if (tid < kRows) {
+                    const int rl = tid / S, f = tid - rl * S, nb = S - 3;
+                    const long long ray = ray0 + rl;
+                    float val = INFINITY;
+                    if (ray < a.R) {
+                        const float u = a.u_f ? a.u_f[ray * Sf + f] : philox_uniform(g.seed, (uint64_t)(ray * Sf + f), 1u);
+                        const float* cdf = i_cdf + rl * S;
+                        const float* t = sm.t_c + rl * S;
+                        int lo = 0, hi = nb + 1;
+                        while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+                        const int below = max(lo - 1, 0), above = min(lo, nb);
+                        const float c0 = cdf[below], c1 = cdf[above];
+                        const float b0 = __fmul_rn(0.5f, __fadd_rn(t[below], t[below + 1]));
+                        const float b1 = __fmul_rn(0.5f, __fadd_rn(t[above], t[above + 1]));
+                        float den = __fsub_rn(c1, c0);
+                        if (den < 1e-5f) den = 1.f;
+                        val = __fadd_rn(b0, __fmul_rn(__fdiv_rn(__fsub_rn(u, c0), den), __fsub_rn(b1, b0)));
+                    }
+                    i_tfu[tid] = val;
+                }
+                __syncthreads();
+                if (tid < kRows) {                                   // rank sort (stable): position = #smaller + #equal-before
+                    const int rl = tid / S, j = tid - rl * S;
+                    const float tj = i_tfu[tid];
+                    const float4* row = reinterpret_cast<const float4*>(i_tfu + rl * S);
+                    int rank = 0;
+#pragma unroll 4
+                    for (int k4 = 0; k4 < S / 4; ++k4) {
+                        const float4 t4 = row[k4];
+                        const int k = 4 * k4;
+                        rank += (t4.x < tj || (t4.x == tj && k + 0 < j)) + (t4.y < tj || (t4.y == tj && k + 1 < j)) +
+                                (t4.z < tj || (t4.z == tj && k + 2 < j)) + (t4.w < tj || (t4.w == tj && k + 3 < j));
+                    }
+                    sm.t_f[rl * Sf + rank] = tj;
                 }
                 __syncthreads();
             }
         }  // pass
 
-        // =================================================================== per-ray weights
+        // =================================================================== per-ray weights, whole CTA
+        // unify_samples (renderer.py:289-301) + weight part of the final MipRayMarcher2 (ray_marcher.py:25-44):
+        //   (1) thread/sample: merged rank (coarse before fine on ties)   (2) thread/interval: alpha
+        //   (3) warp/ray: transmittance scan -> w_i -> omega_j = (w_{j-1}+w_j)/2, ray outputs
+        constexpr int L = S + Sf;
+        float* m_t = scratch;                      // [G][L] merged depths
+        float* m_sg = scratch + 384;               // [G][L] merged densities
+        float* m_alpha = scratch + 768;            // [G][L]
+        float* m_fac = scratch + 1152;             // [G][L]
+        float* m_om = scratch + 1536;              // [G][L] omega per merged position
+        int* m_pos = reinterpret_cast<int*>(scratch + 1920);   // [2][192] merged position of each coarse / fine row
         if (tid < 4 * kRgb) sm.acc[tid >> 5][tid & 31] = 0.f;
-        for (int rl = warp; rl < G; rl += kWarps) {
-            const long long ray = ray0 + rl;
-            if (ray >= a.R) continue;
-            constexpr int L = S + Sf;
-            float* t = scratch + rl * 4 * L;
-            float* sg = t + L;
-            float* w = sg + L;
-            int* src = reinterpret_cast<int*>(w + L);
-            float wsum, dnum;
-            composite_weights<true>(sm.t_c + rl * S, sm.sg_c + rl * S, sm.t_f + rl * Sf, sm.sg_f + rl * Sf, S, Sf, t, sg, w, src, lane, wsum, dnum);
-            for (int j = lane; j < L; j += 32) {
-                const int s = src[j];
-                if (s < S) sm.om_c[rl * S + s] = w[j]; else sm.om_f[rl * Sf + (s - S)] = w[j];
+        for (int r = tid; r < 2 * kRows; r += kThreads) {
+            const bool is_f = r >= kRows;
+            const int row = is_f ? r - kRows : r;
+            const int rl = row / S, i = row - rl * S;
+            const float* tc = sm.t_c + rl * S;
+            const float* tf = sm.t_f + rl * Sf;
+            const bool rev = tc[0] > tc[S - 1];                     // degenerate 'auto' limits: coarse depths descend
+            int pos;
+            float tv, sv;
+            if (!is_f) {
+                const int ci = rev ? S - 1 - i : i;
+                tv = tc[ci]; sv = sm.sg_c[rl * S + ci];
+                int lo = 0, hi = Sf;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (tf[mid] < tv) lo = mid + 1; else hi = mid; }
+                pos = i + lo;
+                m_pos[rl * S + ci] = pos;
+            } else {
+                tv = tf[i]; sv = sm.sg_f[row];
+                int lo = 0, hi = S;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (tc[rev ? S - 1 - mid : mid] <= tv) lo = mid + 1; else hi = mid; }
+                pos = i + lo;
+                m_pos[kRows + row] = pos;
             }
+            m_t[rl * L + pos] = tv; m_sg[rl * L + pos] = sv;
+        }
+        __syncthreads();
+        for (int r = tid; r < 2 * kRows; r += kThreads) {
+            const int rl = r / L, i = r - rl * L;
+            float alpha = 0.f, fac = 1.f;
+            if (i < L - 1) {
+                const float smid = __fsub_rn(__fmul_rn(__fadd_rn(m_sg[r], m_sg[r + 1]), 0.5f), 1.f);
+                alpha = 1.f - ex2_approx(-kLog2e * __fmul_rn(softplus_mufu(smid), m_t[r + 1] - m_t[r]));
+                fac = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+            }
+            m_alpha[r] = alpha; m_fac[r] = fac;
+        }
+        __syncthreads();
+        if (warp < G && ray0 + warp < a.R) {
+            const int rl = warp;
+            const long long ray = ray0 + rl;
+            float carry = 1.f, acc_w = 0.f, acc_d = 0.f, wprev = 0.f;
+#pragma unroll
+            for (int c = 0; c < L / 32; ++c) {
+                const int i = c * 32 + lane;
+                const float incl = warp_scan_mul(m_fac[rl * L + i], lane);
+                float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                if (lane == 0) excl = 1.f;
+                const float wi = m_alpha[rl * L + i] * (carry * excl);      // 0 for i = L-1 (alpha = 0)
+                carry *= __shfl_sync(0xffffffffu, incl, 31);
+                acc_w += wi;
+                if (i < L - 1) acc_d = fmaf(wi, __fmul_rn(__fadd_rn(m_t[rl * L + i], m_t[rl * L + i + 1]), 0.5f), acc_d);
+                float wl = __shfl_up_sync(0xffffffffu, wi, 1);               // w_{i-1}
+                if (lane == 0) wl = wprev;
+                wprev = __shfl_sync(0xffffffffu, wi, 31);
+                m_om[rl * L + i] = __fmul_rn(__fadd_rn(wl, wi), 0.5f);
+            }
+            const float wsum = warp_sum(acc_w), dnum = warp_sum(acc_d);
             const float back = g.white_back ? __fsub_rn(1.f, wsum) : 0.f;
             if (lane < 3) {
                 const float v = fmaf(a.ro[ray * 3 + lane], wsum, a.rd[ray * 3 + lane] * dnum);
@@ -462,8 +597,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_render_fused(const FusedArgs a)
                 sm.ray_back[rl] = back;
                 a.out_depth[ray] = __fdiv_rn(dnum, wsum);
                 a.out_wsum[ray] = wsum;
-                atomicMin(&a.bounds[0], float_to_ordered(t[0]));
-                atomicMax(&a.bounds[1], float_to_ordered(t[L - 1]));
+                atomicMin(&a.bounds[0], float_to_ordered(m_t[rl * L]));
+                atomicMax(&a.bounds[1], float_to_ordered(m_t[rl * L + L - 1]));
             }
         }
         __syncthreads();
@@ -476,7 +611,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_render_fused(const FusedArgs a)
             const int prow = tile * 128 + (warp & 3) * 32 + lane;
             const int rl = prow / S;
             const bool live = ray0 + rl < a.R;
-            const float om = live ? (pass == 0 ? sm.om_c[prow] : sm.om_f[prow]) : 0.f;
+            const float om = live ? m_om[rl * L + m_pos[pass * kRows + prow]] : 0.f;
             const float ca = g.force_sigmoid ? om : 1.002f * om, cb = g.force_sigmoid ? 0.f : -0.001f * om;
             float v[32];
             tmem_ld32(tmem + 64 + kN2 * tt + 1 + lane_base, v);

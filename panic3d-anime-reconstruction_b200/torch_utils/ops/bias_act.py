@@ -37,6 +37,17 @@ _lib.register_protos({
 })
 
 
+def _is_dense(t):
+    """non-overlapping and dense: some permutation of the dims is contiguous (any memory format)."""
+    dims = sorted((st, sz) for st, sz in zip(t.stride(), t.shape) if sz > 1)
+    expect = 1
+    for st, sz in dims:
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
 def _dense_like(t, fmt):
     return t.contiguous(memory_format=fmt)
 
@@ -45,7 +56,7 @@ def _launch(x, b, xref, yref, dy, grad, dim, spec, alpha, gain, clamp):
     """One call of p3d_bias_act; all tensor arguments share x's dense layout (None = absent)."""
     if x.dtype not in _DTYPES:
         raise TypeError(f'bias_act: unsupported dtype {x.dtype}')
-    if not x.is_non_overlapping_and_dense():
+    if not _is_dense(x):
         raise RuntimeError('x must be non-overlapping and dense')
     for name, t in (('xref', xref), ('yref', yref), ('dy', dy)):
         if t is not None and (t.shape != x.shape or t.stride() != x.stride() or t.dtype != x.dtype):
