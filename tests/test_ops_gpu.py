@@ -95,7 +95,15 @@ def test_bias_act_gradients(name):
         return [y] + list(g1) + [g for g in g2]
 
     kw_gpu, kw = kw, _f32_scalars(kw, c['act'])
+    if c['act'] == 'linear' and kw.get('clamp') is not None:
+        # quirk of the reference CUDA path that this op reproduces on purpose: 'linear' saves neither x nor y
+        # (activation_funcs['linear'].ref == '', bias_act.py:24,153-156), so its backward kernel sees yref = 0 and
+        # never gates the gradient by the clamp (bias_act.cu:141-146) - unlike autograd through impl='ref'.
+        y_fwd = oo.bias_act(x.double(), None if b is None else b.double(), **kw)
+        kw = dict(kw, clamp=None)
     ref = run(oo.bias_act, x.double(), None if b is None else b.double(), dy, ddx)
+    if c['act'] == 'linear' and kw_gpu.get('clamp') is not None:
+        ref[0] = y_fwd
     kw = kw_gpu
     got = run(_ba().bias_act, x.double().to(DEV), None if b is None else b.double().to(DEV), dy.to(DEV), ddx.to(DEV))
     for r, g_ in zip(ref, got):
