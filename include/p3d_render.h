@@ -78,6 +78,13 @@ typedef struct p3d_render_params {
     int32_t mlp_mode;         /* P3D_MLP_* */
     /* jitter: when the u_* pointers passed to the call are NULL, uniforms come from Philox(seed) */
     uint64_t seed;
+    /* multi-GPU exactness: the reference clamps composite depth to [min, max] of ALL depths of the batch
+       (ray_marcher.py:50).  With defer_depth_clamp != 0 p3d_render_forward leaves out_depth un-clamped
+       (NaN where the ray accumulated no weight) and stores this rank's (min, max) as two floats at the start of
+       out-of-band device memory `depth_bounds` (see p3d_render_depth_bounds); the host all-reduces them
+       (MIN, MAX) and calls p3d_depth_finalize. */
+    int32_t defer_depth_clamp;
+    int32_t reserved0;
 } p3d_render_params;
 
 const char* p3d_version(void);
@@ -118,6 +125,13 @@ int p3d_render_forward(const p3d_render_params* p, const void* planes,
                        const float* u_coarse, const float* u_fine,
                        void* workspace, size_t workspace_bytes,
                        float* out_rgb, float* out_depth, float* out_wsum, float* out_xyz, void* stream);
+
+/* After a p3d_render_forward with defer_depth_clamp: write this call's (min depth, max depth) as 2 floats to
+   device memory `bounds2` (from the call's workspace). */
+int p3d_render_depth_bounds(const void* workspace, float* bounds2, void* stream);
+
+/* nan_to_num(nan=inf) + clamp(depth, bounds2[0], bounds2[1]) in place, n rays.  ray_marcher.py:49-50. */
+int p3d_depth_finalize(float* depth, int64_t n_rays, const float* bounds2, void* stream);
 
 /* ImportanceRenderer.run_model, renderer.py:266-280 (used by TriPlaneGenerator.sample /
    sample_mixed, triplane.py:254-298, and the 256^3 grid query of _util/eg3d_metrics3d.py:94-183).

@@ -336,7 +336,7 @@ def run_model(planes, dec, xyz, opts, use_triplane, gather='manual'):
 def render(planes: Tensor, dec: Dict, ro: Tensor, rd: Tensor, opts: Dict,
            u_coarse: Tensor, u_fine: Optional[Tensor], use_triplane: bool = True,
            triplane_crop=None, cull_clouds=None, binarize_clouds=None,
-           gather: str = 'manual', depth_bounds: Optional[Tuple[Tensor, Tensor]] = None):
+           gather: str = 'manual', depth_bounds: Optional[Tuple[Tensor, Tensor]] = None, return_bounds: bool = False):
     """ImportanceRenderer.forward, renderer.py:162-264.
     Returns rgb (N,M,32), depth (N,M,1), wsum (N,M,1), xyz (N,M,3)."""
     N, M, _ = ro.shape
@@ -378,7 +378,10 @@ def render(planes: Tensor, dec: Dict, ro: Tensor, rd: Tensor, opts: Dict,
     else:
         d_all, col, sig = d_c, torch.cat([rgb_c, xyz_c], -1), sig_c
     out, depth, w = march(col, sig, d_all, white, lo, hi)
-    return out[..., :-3], depth, w.sum(2), out[..., -3:]
+    res = (out[..., :-3], depth, w.sum(2), out[..., -3:])
+    if return_bounds:          # (min, max) over every depth of this batch: what ray_marcher.py:50 clamps to
+        return res, (d_all.min(), d_all.max())
+    return res
 
 
 # --------------------------------------------------------------------------

@@ -30,6 +30,7 @@ class RenderParams(C.Structure):
         ('w1_gain', C.c_float), ('b1_gain', C.c_float), ('w2_gain', C.c_float), ('b2_gain', C.c_float),
         ('force_sigmoid', C.c_int32), ('mlp_mode', C.c_int32),
         ('seed', C.c_uint64),
+        ('defer_depth_clamp', C.c_int32), ('reserved0', C.c_int32),
     ]
 
 
@@ -49,6 +50,8 @@ _PROTOS = {
     'p3d_render_forward': (C.c_int, [C.POINTER(RenderParams)] + [_VP] * 9 + [_VP, C.c_size_t] + [_VP] * 5),
     'p3d_decode_points': (C.c_int, [C.POINTER(RenderParams)] + [_VP] * 6 + [C.c_int64, _VP, _VP, _VP]),
     'p3d_render_forward_host': (C.c_int, [C.POINTER(RenderParams)] + [_VP] * 7 + [C.c_int32] + [_VP] * 6),
+    'p3d_render_depth_bounds': (C.c_int, [_VP, _VP, _VP]),
+    'p3d_depth_finalize': (C.c_int, [_VP, C.c_int64, _VP, _VP]),
     'p3d_host_arena_release': (None, []),
     'p3d_profile_enable': (None, [C.c_int]),
     'p3d_profile_read': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int, C.c_int]),

@@ -322,6 +322,17 @@ int p3d_render_forward(const p3d_render_params* p, const void* planes, const flo
     return P3D_EUNSUPPORTED;
 }
 
+int p3d_render_depth_bounds(const void* workspace, float* bounds2, void* stream) {
+    P3D_REQUIRE(workspace && bounds2, "null pointer");
+    return launch_bounds_to_float(reinterpret_cast<const unsigned int*>(workspace), bounds2, (cudaStream_t)stream);   // bounds live at offset 0
+}
+
+int p3d_depth_finalize(float* depth, int64_t n_rays, const float* bounds2, void* stream) {
+    P3D_REQUIRE(depth && bounds2 && n_rays >= 0, "bad arguments");
+    if (n_rays == 0) return P3D_OK;
+    return launch_depth_finalize_f(depth, n_rays, bounds2, (cudaStream_t)stream);
+}
+
 int p3d_decode_points(const p3d_render_params* p, const void* planes, const float* w1, const float* b1, const float* w2,
                       const float* b2, const float* coords, int64_t n_points_per_view, float* out_rgb, float* out_sigma,
                       void* stream) {

@@ -710,6 +710,7 @@ int render_forward_fused(const Geom& g, const p3d_render_params* p, const void* 
         kern<<<grid, kThreads, smem, stream>>>(a);
         P3D_LAUNCH_CHECK();
     }
+    if (p->defer_depth_clamp) return P3D_OK;
     return launch_depth_finalize(out_depth, R, ws.bounds, stream);
 }
 

@@ -290,6 +290,17 @@ __global__ void k_depth_finalize(float* depth, long long R, const unsigned int* 
     depth[r] = fminf(fmaxf(d, lo), hi);
 }
 
+__global__ void k_bounds_to_float(const unsigned int* bounds, float* out2) {
+    if (threadIdx.x < 2) out2[threadIdx.x] = ordered_to_float(bounds[threadIdx.x]);
+}
+__global__ void k_depth_finalize_f(float* depth, long long R, const float* bounds2) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    float d = depth[r];
+    if (isnan(d)) d = INFINITY;
+    depth[r] = fminf(fmaxf(d, bounds2[0]), bounds2[1]);
+}
+
 template <int MODE>
 int launch_sample_decode(const SampleArgs& a, bool bf16, cudaStream_t stream) {
     if (a.total <= 0) return P3D_OK;
@@ -312,6 +323,16 @@ int launch_bounds_init(unsigned int* bounds, cudaStream_t stream) {
 }
 int launch_ray_limits(const float* ro, const float* rd, long long R, float h, float* t0, float* t1, unsigned int* bounds, cudaStream_t stream) {
     k_ray_limits<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(ro, rd, R, h, t0, t1, bounds);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+}
+int launch_bounds_to_float(const unsigned int* bounds, float* out2, cudaStream_t stream) {
+    k_bounds_to_float<<<1, 32, 0, stream>>>(bounds, out2);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+}
+int launch_depth_finalize_f(float* depth, long long R, const float* bounds2, cudaStream_t stream) {
+    k_depth_finalize_f<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(depth, R, bounds2);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }
@@ -372,6 +393,7 @@ int render_forward_v1(const Geom& g, const p3d_render_params* p, const void* pla
         k_ray_composite<<<(unsigned)((R + 3) / 4), 128, smem, stream>>>(ca);
         P3D_LAUNCH_CHECK();
     }
+    if (p->defer_depth_clamp) return P3D_OK;
     k_depth_finalize<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(out_depth, R, ws.bounds);
     P3D_LAUNCH_CHECK();
     return P3D_OK;

@@ -88,6 +88,9 @@ class ImportanceRenderer(torch.nn.Module):
         self.mlp_mode = _lib.P3D_MLP_FP32_SIMT     # decoder arithmetic (see include/p3d_render.h)
         self.planes_bf16 = False                   # fast-mode plane storage
         self.injected_noise = None                 # (u_coarse (N,M,S[,1]), u_fine (N*M,Sf)) for parity tests
+        # multi-GPU: callable(bounds2: cuda float tensor [min,max]) reducing the depth-clamp bounds across ranks in
+        # place (panic3d_b200.views.all_reduce_depth_bounds) so a sharded batch clamps like the whole batch would
+        self.depth_bounds_reduce = None
         self._planes = _PlaneCache()
         self._workspace = None
 
@@ -185,11 +188,17 @@ class ImportanceRenderer(torch.nn.Module):
             nbytes = int(L.p3d_render_workspace_bytes(C.byref(p)))
             ws = self._get_workspace(nbytes, dev)
             wt = [t.detach().float().contiguous() for t in (w1, b1, w2, b2)]
+            p.defer_depth_clamp = 1 if self.depth_bounds_reduce is not None else 0
             _lib.check(L.p3d_render_forward(C.byref(p), planes_cl.data_ptr(), wt[0].data_ptr(), wt[1].data_ptr(),
                                             wt[2].data_ptr(), wt[3].data_ptr(), ro.data_ptr(), rd.data_ptr(),
                                             _lib.ptr(u_c), _lib.ptr(u_f), ws.data_ptr(), ws.numel(),
                                             rgb.data_ptr(), depth.data_ptr(), wsum.data_ptr(), xyz.data_ptr(),
                                             _lib.stream_ptr(dev)))
+            if self.depth_bounds_reduce is not None:
+                b2 = torch.empty(2, device=dev, dtype=torch.float32)
+                _lib.check(L.p3d_render_depth_bounds(ws.data_ptr(), b2.data_ptr(), _lib.stream_ptr(dev)))
+                self.depth_bounds_reduce(b2)
+                _lib.check(L.p3d_depth_finalize(depth.data_ptr(), N * M, b2.data_ptr(), _lib.stream_ptr(dev)))
         return rgb, depth, wsum, xyz
 
     # ------------------------------------------------------------------ point queries

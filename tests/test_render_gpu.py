@@ -225,3 +225,31 @@ def test_fused_tc_bf16_fast_mode_is_close(name):
 def test_fused_rejects_unsupported_sampling_loudly():
     with pytest.raises(RuntimeError, match='fused'):
         gpu_render(RENDER_CASES['small_plain'], mlp_mode=1)       # 12+12 samples: no fused kernel -> error, no fallback
+
+
+def test_deferred_depth_clamp_makes_shards_equal_the_batch():
+    """The multi-GPU protocol on one GPU: views rendered one at a time with the batch-wide depth bounds injected
+    through `depth_bounds_reduce` reproduce the batch render exactly (incl. composite depth, ray_marcher.py:50)."""
+    from panic3d_b200.training.volumetric_rendering.renderer import ImportanceRenderer
+    case = RENDER_CASES['small_batch3']
+    dev = _dev()
+    planes, dec, c2w, K, u_c, u_f, opts = build_case_inputs(case)
+    ro, rd = gpu_rays(case, c2w, K, dev)
+    d = make_decoder(dec, dev)
+    M = ro.shape[1]
+    r = ImportanceRenderer(use_triplane=True)
+    seen = {}
+    r.depth_bounds_reduce = lambda b2: seen.__setitem__('b', b2.clone())
+    r.injected_noise = (u_c, u_f)
+    with torch.no_grad():
+        full = r(planes.to(dev), d, ro, rd, opts)
+        parts = []
+        r.depth_bounds_reduce = lambda b2: b2.copy_(seen['b'])
+        for i in range(3):
+            r.injected_noise = (u_c[i:i + 1], u_f[i * M:(i + 1) * M])
+            parts.append(r(planes[i:i + 1].to(dev), d, ro[i:i + 1], rd[i:i + 1], opts))
+    g = load_golden('render', 'small_batch3')
+    for k, key in enumerate(('rgb', 'depth', 'wsum', 'xyz')):
+        cat = torch.cat([p[k] for p in parts])
+        assert torch.equal(cat, full[k]), key
+        assert (cat.cpu() - g[key]).abs().max().item() < TIGHT
