@@ -33,7 +33,7 @@ FLOP_PER_SAMPLE = 2 * 32 * 64 + 2 * 64 * 33            # 8,320 tensor-eligible F
 BYTES_PER_VIEW = 3 * C * P * P * 4 + R * R * 37 * 4    # tri-plane read once + 37 floats/ray out
 
 
-def workload_config(n_gpus, mlp_mode='fp32_simt', planes='fp32'):
+def workload_config(n_gpus, mlp_mode='tc_3xbf16', planes='fp32'):
     return {'workload': f'{VIEWS} views/GPU x {R}x{R} rays x ({S}+{SF}) samples, {VIEWS} distinct 3x{C}x{P}x{P} fp32 tri-planes/GPU',
             'views_per_gpu': VIEWS, 'rays': R * R, 'samples_coarse': S, 'samples_importance': SF, 'plane': P,
             'decoder': '32-64-33 softplus', 'mlp_mode': mlp_mode, 'plane_storage': planes, 'parallelism': f'views sharded x{n_gpus}',
@@ -337,7 +337,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mlp', default=os.environ.get('P3D_BENCH_MLP', 'fp32_simt'), choices=['fp32_simt', 'tc_3xbf16', 'tc_bf16'])
+    ap.add_argument('--mlp', default=os.environ.get('P3D_BENCH_MLP', 'tc_3xbf16'), choices=['fp32_simt', 'tc_3xbf16', 'tc_bf16'])
     ap.add_argument('--planes', default=os.environ.get('P3D_BENCH_PLANES', 'fp32'), choices=['fp32', 'bf16'],
                     help='storage type of the channels-last tri-plane copy the gather reads (bf16 = fast mode, not parity)')
     ap.add_argument('--no-e2e', action='store_true')
