@@ -334,8 +334,8 @@ def run_e2e(L, _lib, planes, decoder, labels, opts, mlp_mode, args, barrier):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--mlp', default=os.environ.get('P3D_BENCH_MLP', 'tc_3xbf16'), choices=['fp32_simt', 'tc_3xbf16', 'tc_bf16'])
     ap.add_argument('--planes', default=os.environ.get('P3D_BENCH_PLANES', 'fp32'), choices=['fp32', 'bf16'],

@@ -184,15 +184,20 @@ __device__ __forceinline__ void plane_taps32(const Geom& g, const FusedArgs& a, 
     reinterpret_cast<int4*>(out)[1] = hi;
 }
 
+// texel quad load: per-lane 64-bit base (view + 4*q channels) + 32-bit element offset.  Written in PTX so the address
+// is ONE mad.wide + the load (nvcc otherwise re-derives every address from the kernel argument with 4 extra ops).
 template <bool BF16>
-__device__ __forceinline__ float4 load_quad32(const void* vbase, int off) {
+__device__ __forceinline__ float4 load_quad32(const void* qbase, int off) {
+    float4 r;
     if (BF16) {
-        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(vbase) + off));
-        return make_float4(__uint_as_float(raw.x << 16), __uint_as_float(raw.x & 0xffff0000u),
-                           __uint_as_float(raw.y << 16), __uint_as_float(raw.y & 0xffff0000u));
+        unsigned int lo, hi;
+        asm("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %3, 2, %2;\n\tld.global.nc.v2.u32 {%0,%1}, [a];\n\t}" : "=r"(lo), "=r"(hi) : "l"(qbase), "r"(off));
+        r = make_float4(__uint_as_float(lo << 16), __uint_as_float(lo & 0xffff0000u), __uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
     } else {
-        return __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(vbase) + off));
+        asm("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %5, 4, %4;\n\tld.global.nc.v4.f32 {%0,%1,%2,%3}, [a];\n\t}"
+            : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(qbase), "r"(off));
     }
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------

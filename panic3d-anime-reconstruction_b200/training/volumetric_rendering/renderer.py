@@ -64,6 +64,7 @@ class _PlaneCache:
     def __init__(self):
         self.key = None
         self.buf = None
+        self.src = None        # strong ref: while cached, the source storage cannot be freed and its address reused
 
     def get(self, planes: torch.Tensor, bf16: bool):
         key = (planes.data_ptr(), planes._version, tuple(planes.shape), tuple(planes.stride()), planes.device, bf16)
@@ -73,7 +74,7 @@ class _PlaneCache:
             buf = torch.empty((N, P, H, W, Cc), device=planes.device, dtype=torch.bfloat16 if bf16 else torch.float32)
             _lib.check(_lib.lib().p3d_planes_to_channels_last(src.data_ptr(), buf.data_ptr(), N * P, Cc, H, W,
                                                              1 if bf16 else 0, _lib.stream_ptr(planes.device)))
-            self.key, self.buf = key, buf
+            self.key, self.buf, self.src = key, buf, planes
         return self.buf
 
 
