@@ -126,6 +126,24 @@ int p3d_render_forward(const p3d_render_params* p, const void* planes,
                        void* workspace, size_t workspace_bytes,
                        float* out_rgb, float* out_depth, float* out_wsum, float* out_xyz, void* stream);
 
+/* Backward of p3d_render_forward (first order) - the autograd counterpart the training loop needs
+   (loss_orthocondA.py:171,279,343,426 -> G.f -> ImportanceRenderer under autograd).  Gradients flow to the
+   tri-plane features and the four decoder tensors; rays, stratified and importance depths (no_grad in the
+   reference, renderer.py:332) and mask-overwritten densities are constants.
+     fwd_workspace   the workspace of the matching p3d_render_forward call with mlp_mode = P3D_MLP_FP32_SIMT,
+                     untouched since (it holds depths, masked densities and colours of every sample)
+     out_depth       that call's out_depth;   g_*  incoming gradients (N,M,32) (N,M) (N,M) (N,M,3)
+     d_planes        (N,3,H,W,C) contiguous fp32, d_w1 (hidden,C), d_b1, d_w2 (out,hidden), d_b2: ZERO-INITIALISED
+                     by the caller, accumulated with atomics; parameter gradients are w.r.t. the raw tensors. */
+size_t p3d_render_backward_scratch_bytes(const p3d_render_params* p);
+int p3d_render_backward(const p3d_render_params* p, const void* planes,
+                        const float* w1, const float* b1, const float* w2, const float* b2,
+                        const float* ray_origins, const float* ray_dirs,
+                        const void* fwd_workspace, size_t fwd_workspace_bytes, const float* out_depth,
+                        const float* g_rgb, const float* g_depth, const float* g_wsum, const float* g_xyz,
+                        void* scratch, size_t scratch_bytes,
+                        float* d_planes, float* d_w1, float* d_b1, float* d_w2, float* d_b2, void* stream);
+
 /* After a p3d_render_forward with defer_depth_clamp: write this call's (min depth, max depth) as 2 floats to
    device memory `bounds2` (from the call's workspace). */
 int p3d_render_depth_bounds(const void* workspace, float* bounds2, void* stream);

@@ -364,7 +364,7 @@ def render(planes: Tensor, dec: Dict, ro: Tensor, rd: Tensor, opts: Dict,
     xyz_c = xyz_c.reshape(N, M, S, 3)
     if Sf > 0:
         _, _, w = march(rgb_c, sig_c, d_c, white, lo, hi)
-        d_f = importance_depths(d_c.reshape(N * M, S), w.reshape(N * M, S - 1), u_fine).reshape(N, M, Sf, 1)
+        d_f = importance_depths(d_c.reshape(N * M, S), w.reshape(N * M, S - 1), u_fine).reshape(N, M, Sf, 1).detach()   # no_grad in the reference (renderer.py:332)
         xyz_f = (ro[:, :, None] + d_f * rd[:, :, None]).reshape(N, -1, 3)
         rgb_f, sig_f = run_model(planes, dec, xyz_f, opts, use_triplane, gather)
         sig_f = apply_masks(sig_f, xyz_f, bw, triplane_crop, cull_clouds, binarize_clouds)

@@ -322,6 +322,30 @@ int p3d_render_forward(const p3d_render_params* p, const void* planes, const flo
     return P3D_EUNSUPPORTED;
 }
 
+size_t p3d_render_backward_scratch_bytes(const p3d_render_params* p) {
+    if (!p) return 0;
+    return (size_t)2 * p->n_views * p->n_rays * ((size_t)p->n_coarse + p->n_fine) * sizeof(float) + 1024;
+}
+
+int p3d_render_backward(const p3d_render_params* p, const void* planes, const float* w1, const float* b1, const float* w2,
+                        const float* b2, const float* ray_origins, const float* ray_dirs, const void* fwd_workspace,
+                        size_t fwd_workspace_bytes, const float* out_depth, const float* g_rgb, const float* g_depth,
+                        const float* g_wsum, const float* g_xyz, void* scratch, size_t scratch_bytes, float* d_planes,
+                        float* d_w1, float* d_b1, float* d_w2, float* d_b2, void* stream) {
+    Geom g;
+    int rc = make_geom(p, &g);
+    if (rc) return rc;
+    P3D_REQUIRE(planes && w1 && b1 && w2 && b2 && ray_origins && ray_dirs && fwd_workspace && out_depth, "null input pointer");
+    P3D_REQUIRE(g_rgb && g_depth && g_wsum && g_xyz, "null gradient pointer (pass zeros for unused outputs)");
+    P3D_REQUIRE(scratch && d_planes && d_w1 && d_b1 && d_w2 && d_b2, "null output pointer");
+    if ((long long)g.N * g.M == 0) return P3D_OK;
+    Workspace ws;
+    const size_t need = workspace_layout(p, const_cast<void*>(fwd_workspace), &ws);
+    if (fwd_workspace_bytes < need) { set_error("forward workspace too small: need %zu bytes", need); return P3D_EWORKSPACE; }
+    return render_backward_v1(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, ws, out_depth, g_rgb, g_depth, g_wsum, g_xyz,
+                              scratch, scratch_bytes, d_planes, d_w1, d_b1, d_w2, d_b2, (cudaStream_t)stream);
+}
+
 int p3d_render_depth_bounds(const void* workspace, float* bounds2, void* stream) {
     P3D_REQUIRE(workspace && bounds2, "null pointer");
     return launch_bounds_to_float(reinterpret_cast<const unsigned int*>(workspace), bounds2, (cudaStream_t)stream);   // bounds live at offset 0

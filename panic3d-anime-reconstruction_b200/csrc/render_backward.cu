@@ -1,0 +1,393 @@
+// Backward of ImportanceRenderer.forward (first order; what the ecrutileE training loop needs:
+// loss_orthocondA.py:171,279,343,426 call G.f -> renderer under autograd; R1's double-backward flows
+// through the discriminator only - SURVEY.md section 3.3).
+//
+// Differentiated: tri-plane features and the four OSGDecoder tensors.  Constants, exactly as in the
+// reference graph: ray origins/directions, stratified depths, the importance depths
+// (sample_importance runs under torch.no_grad, renderer.py:332) and every density that a crop/cull/binarize
+// mask overwrote in place (renderer.py:187-198 - the assignment cuts the graph).
+//
+// Recompute-based, fp32, two kernels on top of the v1 forward's scratch (depths, masked densities, colours):
+//   k_ray_backward     warp per ray: rebuild the merged order and (alpha, T, w); from the incoming
+//                      (d_rgb, d_depth, d_wsum, d_xyz) form dL/dw_i, then dL/dalpha_i via a suffix scan,
+//                      dL/dsigma_j and omega_j per sample  (ray_marcher.py:25-57 differentiated by hand)
+//   k_sample_backward  CTA of 128 samples: re-gather features, re-run the decoder keeping pre-activations
+//                      in smem, back-propagate; weight gradients reduced per CTA in smem then one
+//                      red.global per element; feature gradients scattered to the channels-last
+//                      tri-plane gradient with 128-bit vector atomics (one per tap per 4 channels).
+#include "render_device.cuh"
+
+namespace p3d {
+namespace {
+
+using namespace dev;
+
+constexpr int kT = 128;
+
+struct RayBwdArgs {
+    Geom g;
+    const float *depth_c, *sigma_c, *rgb_c, *depth_f, *sigma_f, *rgb_f, *ro, *rd;
+    const float *g_rgb, *g_depth, *g_wsum, *g_xyz;      // incoming gradients (N*M, 32 | 1 | 1 | 3)
+    const float* out_depth;                              // forward's final (clamped) depth
+    const unsigned int* bounds;
+    float *dsig_c, *om_c, *dsig_f, *om_f;                // per-sample outputs
+    long long R;
+};
+
+__global__ void __launch_bounds__(128) k_ray_backward(const RayBwdArgs a) {
+    extern __shared__ float smem[];
+    const Geom& g = a.g;
+    const int S = g.S, Sf = g.Sf, L = S + Sf, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long ray = (long long)blockIdx.x * 4 + warp;
+    if (ray >= a.R) return;
+    float* t = smem + warp * (8 * L);
+    float* sg = t + L;
+    float* w = sg + L;            // interval weights w_i
+    float* al = w + L;            // alpha_i
+    float* fc = al + L;           // 1 - alpha_i + 1e-10
+    float* Tr = fc + L;           // transmittance T_i
+    float* q = Tr + L;            // g_rgb . c_j per merged sample, later dL/dsigmabar_i
+    int* src = reinterpret_cast<int*>(q + L);
+
+    const float* tc = a.depth_c + ray * S;
+    const float* tf = a.depth_f + ray * Sf;
+    const bool rev = tc[0] > tc[S - 1];
+    for (int i = lane; i < S; i += 32) {
+        const int ci = rev ? S - 1 - i : i;
+        const float v = tc[ci];
+        int lo = 0, hi = Sf;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (tf[mid] < v) lo = mid + 1; else hi = mid; }
+        const int pos = i + lo;
+        t[pos] = v; sg[pos] = a.sigma_c[ray * S + ci]; src[pos] = ci;
+    }
+    for (int j = lane; j < Sf; j += 32) {
+        const float v = tf[j];
+        int lo = 0, hi = S;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (tc[rev ? S - 1 - mid : mid] <= v) lo = mid + 1; else hi = mid; }
+        const int pos = j + lo;
+        t[pos] = v; sg[pos] = a.sigma_f[ray * Sf + j]; src[pos] = S + j;
+    }
+    __syncwarp();
+    // forward quantities per interval
+    float carry = 1.f, acc_w = 0.f, acc_d = 0.f;
+    for (int base = 0; base < L - 1; base += 32) {
+        const int i = base + lane;
+        float alpha = 0.f, factor = 1.f, tmid = 0.f;
+        if (i < L - 1) {
+            const float delta = t[i + 1] - t[i];
+            const float dens = softplus_t(__fsub_rn(__fmul_rn(__fadd_rn(sg[i], sg[i + 1]), 0.5f), 1.f));
+            alpha = 1.f - expf(-__fmul_rn(dens, delta));
+            factor = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+            tmid = __fmul_rn(__fadd_rn(t[i], t[i + 1]), 0.5f);
+        }
+        const float incl = warp_scan_mul(factor, lane);
+        float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) excl = 1.f;
+        const float T = carry * excl;
+        const float wi = alpha * T;
+        if (i < L - 1) { w[i] = wi; al[i] = alpha; fc[i] = factor; Tr[i] = T; acc_w += wi; acc_d = fmaf(wi, tmid, acc_d); }
+        carry *= __shfl_sync(0xffffffffu, incl, 31);
+    }
+    const float W = warp_sum(acc_w), D = warp_sum(acc_d);
+    __syncwarp();
+    // q_j = g_rgb . c_j   (lane = channel)
+    const float grgb = a.g_rgb[ray * kRgb + lane];
+    for (int j = 0; j < L; ++j) {
+        const int s = src[j];
+        const float c = s < S ? a.rgb_c[(ray * S + s) * kRgb + lane] : a.rgb_f[(ray * Sf + (s - S)) * kRgb + lane];
+        const float d = warp_sum(grgb * c);
+        if (lane == 0) q[j] = d;
+    }
+    const float grgb_sum = warp_sum(grgb);
+    float gx_o = 0.f, gx_d = 0.f, gx_sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float gk = a.g_xyz[ray * 3 + k];
+        gx_o = fmaf(gk, a.ro[ray * 3 + k], gx_o); gx_d = fmaf(gk, a.rd[ray * 3 + k], gx_d); gx_sum += gk;
+    }
+    // depth = clamp(nan_to_num(D/W)): gradient only where the value is finite and strictly inside the clamp range
+    const float lo_b = ordered_to_float(a.bounds[0]), hi_b = ordered_to_float(a.bounds[1]);
+    const float depth_raw = D / W;
+    const bool depth_live = (W != 0.f) && !isnan(depth_raw) && depth_raw >= lo_b && depth_raw <= hi_b;
+    const float gdep = depth_live ? a.g_depth[ray] : 0.f;
+    const float gW = a.g_wsum[ray];
+    const float back = g.white_back ? 1.f : 0.f;
+    const float common = gW - 2.f * back * (grgb_sum + gx_sum) + 2.f * gx_o;
+    __syncwarp();
+    // dL/dw_i = P_i ; prefix sums of w_i P_i for the suffix term
+    float pcarry = 0.f;
+    float total = 0.f;
+    for (int pass = 0; pass < 2; ++pass) {
+        pcarry = 0.f;
+        for (int base = 0; base < L - 1; base += 32) {
+            const int i = base + lane;
+            float P = 0.f, wP = 0.f;
+            if (i < L - 1) {
+                const float tmid = __fmul_rn(__fadd_rn(t[i], t[i + 1]), 0.5f);
+                P = (q[i] + q[i + 1]) + 2.f * gx_d * tmid + common + (depth_live ? gdep * (tmid - depth_raw) / W : 0.f);
+                wP = w[i] * P;
+            }
+            const float incl = warp_scan_add(wP, lane) + pcarry;
+            pcarry = __shfl_sync(0xffffffffu, incl, 31);
+            if (pass == 1 && i < L - 1) {
+                const float suffix = total - incl;                              // sum_{k>i} w_k P_k
+                const float dalpha = Tr[i] * P - suffix / fc[i];
+                const float smid = __fsub_rn(__fmul_rn(__fadd_rn(sg[i], sg[i + 1]), 0.5f), 1.f);
+                const float dsp = smid > 20.f ? 1.f : sigmoid_t(smid);          // d softplus
+                al[i] = dalpha * (1.f - al[i]) * (t[i + 1] - t[i]) * dsp;       // dL/dsigmabar_i (reuse al[])
+            }
+        }
+        if (pass == 0) total = pcarry;
+    }
+    __syncwarp();
+    // per sample: dsigma_j = (dsb_{j-1} + dsb_j)/2 ; omega_j = (w_{j-1} + w_j)/2
+    for (int j = lane; j < L; j += 32) {
+        const float dl = j > 0 ? al[j - 1] : 0.f, dr = j < L - 1 ? al[j] : 0.f;
+        const float wl = j > 0 ? w[j - 1] : 0.f, wr = j < L - 1 ? w[j] : 0.f;
+        const float ds = 0.5f * (dl + dr), om = 0.5f * (wl + wr);
+        const int s = src[j];
+        if (s < S) { a.dsig_c[ray * S + s] = ds; a.om_c[ray * S + s] = om; }
+        else { a.dsig_f[ray * Sf + (s - S)] = ds; a.om_f[ray * Sf + (s - S)] = om; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct SampleBwdArgs {
+    Geom g;
+    const void* planes;
+    const float *w1, *b1, *w2, *b2;
+    const float *ro, *rd;
+    const float* depth;          // (R*per_ray) depths of this pass
+    const float* dsig;           // dL/dsigma (post-mask) per sample
+    const float* omega;          // omega per sample
+    const float* g_rgb;          // (R,32)
+    float* d_planes;             // (N,3,H,W,32) contiguous fp32 gradient (its own canonical strides)
+    float *d_w1, *d_b1, *d_w2, *d_b2;   // gradients w.r.t. the RAW parameters (gains folded in)
+    long long total;
+    int per_ray;
+};
+
+constexpr int kXs = 33, kHs = 65, kDs = 36;
+constexpr size_t kBwdSmemFloats = (size_t)kHidden * kC + kOut * kHidden + kHidden + 36 +
+                                  (size_t)kT * (kXs + kHs + kHs + kDs + kHs + kXs) + kT * 12 * 2 + kT * 2 + kT;
+
+// texel indices (p*H*W + y*W + x, or -1) and bilinear weights of one plane; same arithmetic as dev::plane_taps
+__device__ __forceinline__ void tap_texels(const Geom& g, int plane, float ca, float cb, int2* out) {
+    const float gx = __fmul_rn(ca, g.coord_scale), gy = __fmul_rn(cb, g.coord_scale);
+    const float fx = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)g.W), 1.f), 0.5f);
+    const float fy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)g.H), 1.f), 0.5f);
+    const bool sane = (fx > -2.f) && (fx < (float)g.W + 1.f) && (fy > -2.f) && (fy < (float)g.H + 1.f);
+    const float x0f = floorf(fx), y0f = floorf(fy);
+    const float wx1 = fx - x0f, wy1 = fy - y0f, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    const int x0 = sane ? (int)x0f : -4, y0 = sane ? (int)y0f : -4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int xi = x0 + (k & 1), yi = y0 + (k >> 1);
+        const bool ok = (xi >= 0) && (xi < g.W) && (yi >= 0) && (yi < g.H);
+        const float wgt = ((k & 1) ? wx1 : wx0) * ((k >> 1) ? wy1 : wy0);
+        out[k] = make_int2(ok ? (plane * g.H + yi) * g.W + xi : -1, __float_as_int(ok ? wgt : 0.f));
+    }
+}
+
+template <bool BF16>
+__global__ void __launch_bounds__(kT) k_sample_backward(const SampleBwdArgs a) {
+    extern __shared__ float sm[];
+    float* s_w1 = sm;                        // [64][32]  effective (gain folded)
+    float* s_w2 = s_w1 + kHidden * kC;       // [33][64]
+    float* s_b1 = s_w2 + kOut * kHidden;     // [64]
+    float* s_b2 = s_b1 + kHidden;            // [36]
+    float* s_x = s_b2 + 36;                  // [128][33] features
+    float* s_pre = s_x + kT * kXs;           // [128][65] pre-activations
+    float* s_hs = s_pre + kT * kHs;          // [128][65] softplus(pre)
+    float* s_do = s_hs + kT * kHs;           // [128][36] d_logits
+    float* s_dp = s_do + kT * kDs;           // [128][65] d_pre
+    float* s_dx = s_dp + kT * kHs;           // [128][33] d_features (already / 3)
+    int2* s_tap = reinterpret_cast<int2*>(s_dx + kT * kXs);   // [128][12]
+    float* s_xz = reinterpret_cast<float*>(s_tap + kT * 12);  // [128][2]
+    int* s_view = reinterpret_cast<int*>(s_xz + kT * 2);      // [128]
+
+    const Geom& g = a.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long tile0 = (long long)blockIdx.x * kT;
+    for (int i = tid; i < kHidden * kC; i += kT) s_w1[i] = __fmul_rn(a.w1[i], g.w1_gain);
+    for (int i = tid; i < kOut * kHidden; i += kT) s_w2[i] = __fmul_rn(a.w2[i], g.w2_gain);
+    if (tid < kHidden) s_b1[tid] = __fmul_rn(a.b1[tid], g.b1_gain);
+    if (tid < kOut) s_b2[tid] = __fmul_rn(a.b2[tid], g.b2_gain);
+
+    // ---- A) positions, tap records (for the scatter), features
+    {
+        const int sub = lane >> 3, qd = lane & 7;
+        for (int round = 0; round < 8; ++round) {
+            const int local = warp * 32 + round * 4 + sub;
+            const long long gidx = tile0 + local;
+            float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+            float px = 0.f, pz = 0.f;
+            int view = 0;
+            const bool ok = gidx < a.total;
+            float py = 0.f;
+            if (ok) {
+                const long long ray = gidx / a.per_ray;
+                view = (int)(ray / g.M);
+                const float tval = a.depth[gidx];
+                const float* o = a.ro + ray * 3;
+                const float* d = a.rd + ray * 3;
+                px = __fadd_rn(o[0], __fmul_rn(tval, d[0]));
+                py = __fadd_rn(o[1], __fmul_rn(tval, d[1]));
+                pz = __fadd_rn(o[2], __fmul_rn(tval, d[2]));
+                f = gather_features<BF16>(a.planes, g, view, px, py, pz, qd);
+            }
+            if (qd < 3) {                                         // lanes 0..2 of a sample record plane qd's taps
+                if (ok) {
+                    const bool pm = g.plane_mode == P3D_PLANES_PANIC3D;
+                    const float ca = qd == 2 ? (pm ? py : pz) : px;
+                    const float cb = qd == 0 ? py : (qd == 1 ? pz : (pm ? pz : px));
+                    tap_texels(g, qd, ca, cb, s_tap + local * 12 + qd * 4);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) s_tap[local * 12 + qd * 4 + k] = make_int2(-1, 0);
+                }
+            }
+            float* dst = s_x + local * kXs + 4 * qd;
+            dst[0] = f.x; dst[1] = f.y; dst[2] = f.z; dst[3] = f.w;
+            if (qd == 0) { s_xz[local * 2] = px; s_xz[local * 2 + 1] = pz; s_view[local] = view; }
+        }
+    }
+    __syncthreads();
+    // ---- B) decoder forward, thread per sample; C) d_logits; D) back through the two layers
+    {
+        const long long gidx = tile0 + tid;
+        const bool live = gidx < a.total;
+        float o[kOut];
+#pragma unroll
+        for (int m = 0; m < kOut; ++m) o[m] = s_b2[m];
+        float x[kC];
+#pragma unroll
+        for (int k = 0; k < kC; ++k) x[k] = s_x[tid * kXs + k];
+        for (int j = 0; j < kHidden; ++j) {
+            float h = s_b1[j];
+#pragma unroll
+            for (int k = 0; k < kC; ++k) h = fmaf(x[k], s_w1[j * kC + k], h);
+            const float hs = softplus_t(h);
+            s_pre[tid * kHs + j] = h;
+            s_hs[tid * kHs + j] = hs;
+#pragma unroll
+            for (int m = 0; m < kOut; ++m) o[m] = fmaf(hs, s_w2[m * kHidden + j], o[m]);
+        }
+        float dsg = 0.f, om = 0.f;
+        long long ray = 0;
+        if (live) { dsg = a.dsig[gidx]; om = a.omega[gidx]; ray = gidx / a.per_ray; }
+        // a density overwritten by a crop/cull/binarize mask is a constant of the reference graph
+        if (apply_masks(g, o[0], s_xz[tid * 2], s_xz[tid * 2 + 1]) != o[0]) dsg = 0.f;
+        float dlog[kOut];
+        dlog[0] = dsg;
+#pragma unroll
+        for (int c = 0; c < kRgb; ++c) {
+            const float sgm = sigmoid_t(o[1 + c]);
+            const float dcol = live ? 2.f * om * a.g_rgb[ray * kRgb + c] : 0.f;          // d rgb / d c_j = 2 * omega_j
+            dlog[1 + c] = dcol * (g.force_sigmoid ? 1.f : 1.002f) * sgm * (1.f - sgm);
+        }
+#pragma unroll
+        for (int m = 0; m < kOut; ++m) s_do[tid * kDs + m] = dlog[m];
+        float dx[kC];
+#pragma unroll
+        for (int k = 0; k < kC; ++k) dx[k] = 0.f;
+        for (int j = 0; j < kHidden; ++j) {
+            float dh = 0.f;
+#pragma unroll
+            for (int m = 0; m < kOut; ++m) dh = fmaf(dlog[m], s_w2[m * kHidden + j], dh);
+            const float pre = s_pre[tid * kHs + j];
+            const float dpre = dh * (pre > 20.f ? 1.f : sigmoid_t(pre));
+            s_dp[tid * kHs + j] = dpre;
+#pragma unroll
+            for (int k = 0; k < kC; ++k) dx[k] = fmaf(dpre, s_w1[j * kC + k], dx[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < kC; ++k) s_dx[tid * kXs + k] = dx[k] * (1.f / 3.f);            // d(mean over 3 planes)
+    }
+    __syncthreads();
+    // ---- E) parameter gradients: reduce over the CTA's 128 samples, one red.global per element
+    for (int e = tid; e < kOut * kHidden; e += kT) {                 // dW2[m][j] = sum_s dlog[s][m] * hs[s][j]
+        const int m = e / kHidden, j = e - m * kHidden;
+        float acc = 0.f;
+        for (int sidx = 0; sidx < kT; ++sidx) acc = fmaf(s_do[sidx * kDs + m], s_hs[sidx * kHs + j], acc);
+        atomicAdd(a.d_w2 + e, acc * g.w2_gain);
+    }
+    for (int e = tid; e < kHidden * kC; e += kT) {                   // dW1[j][k] = sum_s dpre[s][j] * x[s][k]
+        const int j = e / kC, k = e - j * kC;
+        float acc = 0.f;
+        for (int sidx = 0; sidx < kT; ++sidx) acc = fmaf(s_dp[sidx * kHs + j], s_x[sidx * kXs + k], acc);
+        atomicAdd(a.d_w1 + e, acc * g.w1_gain);
+    }
+    if (tid < kOut) {
+        float acc = 0.f;
+        for (int sidx = 0; sidx < kT; ++sidx) acc += s_do[sidx * kDs + tid];
+        atomicAdd(a.d_b2 + tid, acc * g.b2_gain);
+    }
+    if (tid >= 64 && tid < 64 + kHidden) {
+        const int j = tid - 64;
+        float acc = 0.f;
+        for (int sidx = 0; sidx < kT; ++sidx) acc += s_dp[sidx * kHs + j];
+        atomicAdd(a.d_b1 + j, acc * g.b1_gain);
+    }
+    // ---- F) scatter d_features to the tri-plane gradient: 8 lanes x float4 per tap
+    {
+        const int sub = lane >> 3, qd = lane & 7;
+        const long long plane_elems = (long long)3 * g.H * g.W * kC;
+        for (int round = 0; round < 8; ++round) {
+            const int local = warp * 32 + round * 4 + sub;
+            if (tile0 + local >= a.total) continue;
+            const float* dxr = s_dx + local * kXs + 4 * qd;
+            const float4 dv = make_float4(dxr[0], dxr[1], dxr[2], dxr[3]);
+            float* base = a.d_planes + (long long)s_view[local] * plane_elems + 4 * qd;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) {
+                const int2 tp = s_tap[local * 12 + k];
+                if (tp.x < 0) continue;
+                const float wgt = __int_as_float(tp.y);
+                atomicAdd(reinterpret_cast<float4*>(base + (long long)tp.x * kC), make_float4(dv.x * wgt, dv.y * wgt, dv.z * wgt, dv.w * wgt));
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int render_backward_v1(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
+                       const float* w2, const float* b2, const float* ro, const float* rd, const Workspace& ws,
+                       const float* out_depth, const float* g_rgb, const float* g_depth, const float* g_wsum,
+                       const float* g_xyz, void* scratch, size_t scratch_bytes, float* d_planes, float* d_w1, float* d_b1,
+                       float* d_w2, float* d_b2, cudaStream_t stream) {
+    const long long R = (long long)g.N * g.M;
+    const size_t per = (size_t)R * (g.S + g.Sf) * sizeof(float);
+    if (scratch_bytes < 2 * per + 1024) { set_error("backward scratch too small: need %zu bytes", 2 * per + 1024); return P3D_EWORKSPACE; }
+    float* dsig_c = reinterpret_cast<float*>(scratch);
+    float* dsig_f = dsig_c + (size_t)R * g.S;
+    float* om_c = dsig_f + (size_t)R * g.Sf;
+    float* om_f = om_c + (size_t)R * g.S;
+    RayBwdArgs ra{};
+    ra.g = g; ra.depth_c = ws.depth_c; ra.sigma_c = ws.sigma_c; ra.rgb_c = ws.rgb_c; ra.depth_f = ws.depth_f; ra.sigma_f = ws.sigma_f;
+    ra.rgb_f = ws.rgb_f; ra.ro = ro; ra.rd = rd; ra.g_rgb = g_rgb; ra.g_depth = g_depth; ra.g_wsum = g_wsum; ra.g_xyz = g_xyz;
+    ra.out_depth = out_depth; ra.bounds = ws.bounds; ra.dsig_c = dsig_c; ra.om_c = om_c; ra.dsig_f = dsig_f; ra.om_f = om_f; ra.R = R;
+    const size_t smem_ray = (size_t)4 * 8 * (g.S + g.Sf) * sizeof(float);
+    if (smem_ray > 48 * 1024) P3D_CUDA_TRY(cudaFuncSetAttribute(k_ray_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_ray));
+    k_ray_backward<<<(unsigned)((R + 3) / 4), 128, smem_ray, stream>>>(ra);
+    P3D_LAUNCH_CHECK();
+    const size_t smem = kBwdSmemFloats * sizeof(float);
+    auto kern = p->planes_bf16 ? k_sample_backward<true> : k_sample_backward<false>;
+    P3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int pass = 0; pass < 2; ++pass) {
+        const int per_ray = pass == 0 ? g.S : g.Sf;
+        if (per_ray == 0) continue;
+        SampleBwdArgs sa{};
+        sa.g = g; sa.planes = planes; sa.w1 = w1; sa.b1 = b1; sa.w2 = w2; sa.b2 = b2; sa.ro = ro; sa.rd = rd;
+        sa.depth = pass == 0 ? ws.depth_c : ws.depth_f; sa.dsig = pass == 0 ? dsig_c : dsig_f; sa.omega = pass == 0 ? om_c : om_f;
+        sa.g_rgb = g_rgb; sa.d_planes = d_planes; sa.d_w1 = d_w1; sa.d_b1 = d_b1; sa.d_w2 = d_w2; sa.d_b2 = d_b2;
+        sa.total = R * per_ray; sa.per_ray = per_ray;
+        const long long blocks = (sa.total + kT - 1) / kT;
+        kern<<<(unsigned)blocks, kT, smem, stream>>>(sa);
+        P3D_LAUNCH_CHECK();
+    }
+    return P3D_OK;
+}
+
+}  // namespace p3d

@@ -50,6 +50,11 @@ int render_forward_v1(const Geom& g, const p3d_render_params* p, const void* pla
                       const float* w2, const float* b2, const float* ro, const float* rd, const float* u_c,
                       const float* u_f, const Workspace& ws, float* out_rgb, float* out_depth, float* out_wsum,
                       float* out_xyz, cudaStream_t stream);
+int render_backward_v1(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
+                       const float* w2, const float* b2, const float* ro, const float* rd, const Workspace& ws,
+                       const float* out_depth, const float* g_rgb, const float* g_depth, const float* g_wsum,
+                       const float* g_xyz, void* scratch, size_t scratch_bytes, float* d_planes, float* d_w1, float* d_b1,
+                       float* d_w2, float* d_b2, cudaStream_t stream);
 int launch_bounds_to_float(const unsigned int* bounds, float* out2, cudaStream_t stream);
 int launch_depth_finalize_f(float* depth, long long R, const float* bounds2, cudaStream_t stream);
 // fused: one persistent kernel, OSGDecoder on tcgen05 tensor cores (3-pass split bf16 or single-pass bf16).

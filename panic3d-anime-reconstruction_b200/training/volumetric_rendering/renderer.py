@@ -78,6 +78,64 @@ class _PlaneCache:
         return self.buf
 
 
+class _RenderFunction(torch.autograd.Function):
+    """Training path: fp32 SIMT forward (keeps its per-sample scratch) + p3d_render_backward.  Gradients reach
+    the tri-planes and the four decoder tensors; rays and the (no_grad) importance depths are constants, as in
+    the reference graph (renderer.py:332)."""
+
+    @staticmethod
+    def forward(ctx, renderer, planes, w1, b1, w2, b2, ro, rd, p, noise):
+        dev = planes.device
+        L = _lib.lib()
+        N, M = p.n_views, p.n_rays
+        # the backward scatters into a canonical (N,3,H,W,C) buffer, so the forward reads the same layout
+        src = planes.detach().float()
+        planes_cl = torch.empty((N, 3, p.plane_h, p.plane_w, p.channels), device=dev, dtype=torch.float32)
+        srcc = src if src.is_contiguous() else src.contiguous()
+        _lib.check(L.p3d_planes_to_channels_last(srcc.data_ptr(), planes_cl.data_ptr(), N * 3, p.channels, p.plane_h, p.plane_w, 0,
+                                                 _lib.stream_ptr(dev)))
+        sv, sp, sr, sc, _ = planes_cl.stride()
+        p.stride_view, p.stride_plane, p.stride_row, p.stride_col, p.planes_bf16 = sv, sp, sr, sc, 0
+        p.mlp_mode = _lib.P3D_MLP_FP32_SIMT
+        wt = [t.detach().float().contiguous() for t in (w1, b1, w2, b2)]
+        ro, rd = ro.detach().float().contiguous(), rd.detach().float().contiguous()
+        u_c, u_f = noise
+        out = [torch.empty(sh, device=dev, dtype=torch.float32) for sh in ((N, M, p.out_dim - 1), (N, M, 1), (N, M, 1), (N, M, 3))]
+        ws = torch.empty(int(L.p3d_render_workspace_bytes(C.byref(p))), dtype=torch.uint8, device=dev)
+        _lib.check(L.p3d_render_forward(C.byref(p), planes_cl.data_ptr(), *[t.data_ptr() for t in wt], ro.data_ptr(), rd.data_ptr(),
+                                        _lib.ptr(u_c), _lib.ptr(u_f), ws.data_ptr(), ws.numel(), *[o.data_ptr() for o in out],
+                                        _lib.stream_ptr(dev)))
+        if p.defer_depth_clamp:
+            b2_ = torch.empty(2, device=dev, dtype=torch.float32)
+            _lib.check(L.p3d_render_depth_bounds(ws.data_ptr(), b2_.data_ptr(), _lib.stream_ptr(dev)))
+            renderer.depth_bounds_reduce(b2_)
+            _lib.check(L.p3d_depth_finalize(out[1].data_ptr(), N * M, b2_.data_ptr(), _lib.stream_ptr(dev)))
+        ctx.save_for_backward(planes_cl, *wt, ro, rd, ws, out[1])
+        ctx.p = p
+        ctx.in_dtypes = (planes.dtype, w1.dtype, b1.dtype, w2.dtype, b2.dtype)
+        return tuple(out)
+
+    @staticmethod
+    def backward(ctx, g_rgb, g_depth, g_wsum, g_xyz):
+        planes_cl, w1, b1, w2, b2, ro, rd, ws, depth = ctx.saved_tensors
+        p, dev, L = ctx.p, planes_cl.device, _lib.lib()
+        N, M = p.n_views, p.n_rays
+        z = lambda g_, sh: (torch.zeros(sh, device=dev, dtype=torch.float32) if g_ is None else g_.float().contiguous())
+        g_rgb, g_depth, g_wsum, g_xyz = z(g_rgb, (N, M, p.out_dim - 1)), z(g_depth, (N, M, 1)), z(g_wsum, (N, M, 1)), z(g_xyz, (N, M, 3))
+        d_planes = torch.zeros_like(planes_cl)
+        d_w = [torch.zeros_like(t) for t in (w1, b1, w2, b2)]
+        scratch = torch.empty(int(L.p3d_render_backward_scratch_bytes(C.byref(p))), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.p3d_render_backward(C.byref(p), planes_cl.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+                                             ro.data_ptr(), rd.data_ptr(), ws.data_ptr(), ws.numel(), depth.data_ptr(),
+                                             g_rgb.data_ptr(), g_depth.data_ptr(), g_wsum.data_ptr(), g_xyz.data_ptr(),
+                                             scratch.data_ptr(), scratch.numel(), d_planes.data_ptr(), *[t.data_ptr() for t in d_w],
+                                             _lib.stream_ptr(dev)))
+        dts = ctx.in_dtypes
+        return (None, d_planes.permute(0, 1, 4, 2, 3).to(dts[0]), d_w[0].to(dts[1]), d_w[1].to(dts[2]), d_w[2].to(dts[3]),
+                d_w[3].to(dts[4]), None, None, None, None)
+
+
 class ImportanceRenderer(torch.nn.Module):
     """Reference: renderer.py:156-387.  Parameter-free, like the reference."""
 
@@ -160,11 +218,12 @@ class ImportanceRenderer(torch.nn.Module):
                 triplane_crop=None, cull_clouds=None, binarize_clouds=None):
         """-> rgb (N,M,32), depth (N,M,1), weights_sum (N,M,1), xyz (N,M,3).  Reference renderer.py:162-264."""
         self._require_cuda(planes, ray_origins, ray_directions)
-        if torch.is_grad_enabled() and (planes.requires_grad or any(q.requires_grad for q in decoder.parameters())):
-            raise NotImplementedError('ImportanceRenderer backward is not implemented yet; call under torch.no_grad()')
         dev = planes.device
         self.plane_axes = self.plane_axes.to(dev)
         N, M, _ = ray_origins.shape
+        if torch.is_grad_enabled() and (planes.requires_grad or any(q.requires_grad for q in decoder.parameters())):
+            return self._forward_autograd(planes, decoder, ray_origins, ray_directions, rendering_options, triplane_crop,
+                                          cull_clouds, binarize_clouds)
         with torch.cuda.device(dev):
             planes_cl = self._planes_cl(planes.detach())
             p, (w1, b1, w2, b2) = self._params(planes_cl, N, M, rendering_options, decoder, triplane_crop, cull_clouds,
@@ -201,6 +260,31 @@ class ImportanceRenderer(torch.nn.Module):
                 self.depth_bounds_reduce(b2)
                 _lib.check(L.p3d_depth_finalize(depth.data_ptr(), N * M, b2.data_ptr(), _lib.stream_ptr(dev)))
         return rgb, depth, wsum, xyz
+
+    def _noise(self, dev, N, M, p):
+        if self.injected_noise is None:
+            return None, None
+        u_c, u_f = self.injected_noise
+        u_c = u_c.to(dev, torch.float32).contiguous()
+        assert u_c.numel() == N * M * p.n_coarse, 'u_coarse shape'
+        if p.n_fine > 0:
+            u_f = u_f.to(dev, torch.float32).contiguous()
+            assert u_f.numel() == N * M * p.n_fine, 'u_fine shape'
+        else:
+            u_f = None
+        return u_c, u_f
+
+    def _forward_autograd(self, planes, decoder, ray_origins, ray_directions, rendering_options, triplane_crop, cull_clouds,
+                          binarize_clouds):
+        dev = planes.device
+        N, M, _ = ray_origins.shape
+        if planes.dim() != 5 or planes.shape[1] != 3:
+            raise ValueError(f'planes must be (N,3,C,H,W), got {tuple(planes.shape)}')
+        with torch.cuda.device(dev):
+            shape_probe = torch.empty((N, 3, planes.shape[3], planes.shape[4], planes.shape[2]), device='meta')
+            p, (w1, b1, w2, b2) = self._params(shape_probe, N, M, rendering_options, decoder, triplane_crop, cull_clouds, binarize_clouds)
+            p.defer_depth_clamp = 1 if self.depth_bounds_reduce is not None else 0
+            return _RenderFunction.apply(self, planes, w1, b1, w2, b2, ray_origins, ray_directions, p, self._noise(dev, N, M, p))
 
     # ------------------------------------------------------------------ point queries
     def run_model(self, planes, decoder, sample_coordinates, sample_directions, options):
