@@ -1,5 +1,6 @@
 // extern "C" surface of libp3d.so (see include/p3d_render.h) + small utility kernels.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include <mutex>
 #include <vector>
@@ -315,6 +316,12 @@ int p3d_render_forward(const p3d_render_params* p, const void* planes, const flo
     if (p->mlp_mode == P3D_MLP_FP32_SIMT)
         return render_forward_v1(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
                                  out_depth, out_wsum, out_xyz, (cudaStream_t)stream);
+    if (p->mlp_mode == P3D_MLP_TC_3XBF16 || p->mlp_mode == P3D_MLP_TC_BF16) {
+        static const char* impl = getenv("P3D_FUSED_IMPL");       // "v2": 2-CTA/SM bulk-synchronous kernel; default: warp-specialised
+        if (!(impl && impl[0] == 'v' && impl[1] == '2') && fused_ws_supported(g))
+            return render_forward_fused_ws(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
+                                           out_depth, out_wsum, out_xyz, (cudaStream_t)stream);
+    }
     if (p->mlp_mode == P3D_MLP_TC_3XBF16 || p->mlp_mode == P3D_MLP_TC_BF16)
         return render_forward_fused(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
                                     out_depth, out_wsum, out_xyz, (cudaStream_t)stream);

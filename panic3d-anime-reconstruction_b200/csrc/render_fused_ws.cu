@@ -1,0 +1,777 @@
+// Warp-specialised fused renderer (v3): one persistent CTA per SM, 19 warps in four roles, two ray groups in
+// flight, every hand-off through mbarriers.
+//
+//   warps  0- 7  GATHER    per tile: 16 rows each; taps -> 12 x 128-bit loads per lane -> lerp -> bf16 hi/lo A1 tile
+//   warps  8-15  EPILOGUE  per tile: tcgen05.ld D1 -> softplus2 -> A2 tile; sigma read-back; at group end the
+//                          colour reduction straight out of TMEM
+//   warps 16-17  RAYS      per group: importance sampling after the coarse pass, merge/transmittance after the fine
+//   warp  18     MMA       one thread: layer-1 (N=64) and layer-2 (N=32 colour + N=16 sigma) tcgen05.mma, commits
+//
+// A ray group is 384/S rays (4 at S=Sf=96, 8 at 48); a pass over it is three full 128-row tiles, tile k holding
+// samples [k*S/3, (k+1)*S/3) of every ray, so a TMEM lane quarter is one ray's 32 consecutive samples.
+// The gather warps walk the tile sequence  C(A) C(B) F(A) F(B) | C(A') C(B') F(A') F(B') | ...  (C = coarse
+// tiles, F = importance tiles): every dependency - importance depths for F(A), TMEM/state reuse for C(A') - has
+// three tiles of independent gather work in front of it, so the loads never stop.  Colour logits of both groups
+// stay in TMEM (2 x 6 tiles x 32 columns) next to D1 (64) and the sigma accumulator (16): 464 of 512 columns.
+#include "render_device.cuh"
+
+namespace p3d {
+
+namespace {
+
+using namespace dev;
+
+constexpr int kGW = 8, kEW = 8, kRW = 2;
+constexpr int kWarpsWS = kGW + kEW + kRW + 1;
+constexpr int kThreadsWS = kWarpsWS * 32;        // 608
+constexpr int kNA = 3;                           // A1 ring depth
+constexpr int kStates = 4;                       // per-group state ring
+constexpr int kRowsG = 384;                      // rows per pass per group
+constexpr int kTmemColsWS = 512;
+constexpr int kColD1 = 0, kColSig = 64, kColD2 = 96;   // D2[slot][tile6] = 96 + (slot*6 + tile6)*32
+
+constexpr int kSBO = 128, kLBO_A = 2048, kLBO_W1 = 1024, kLBO_W2C = 512, kLBO_W2S = 256;
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+struct GroupState {                               // written by G (t_c, crop), E (sg_*), R (t_f)
+    float t_c[kRowsG], sg_c[kRowsG], t_f[kRowsG], sg_f[kRowsG];
+    unsigned char crop[2][kRowsG];
+};
+struct SlotState {                                // written by R (composite), read by E (colours)
+    float om[2 * kRowsG];                         // omega per merged position, [ray][2S]
+    int pos[2 * kRowsG];                          // merged position of coarse rows [0,384) and fine rows [384,768)
+    float acc[8][kRgb];
+    float back[8];
+};
+
+struct __align__(1024) WsSmem {
+    unsigned char a1[kNA][2][8192];
+    unsigned char a2[2][2][16384];
+    unsigned char w1[2][4096], w2c[2][4096], w2s[2][2048];
+    float b1[kHidden], b2c[kRgb], b2s, pad0[3];
+    int2 taps[kGW][16][12];
+    GroupState st[kStates];
+    SlotState slot[2];
+    float rscratch[kRW][1536];
+    unsigned long long a1_full[kNA], a1_empty[kNA], a2_full[2], a2_empty[2];
+    unsigned long long d1_full, d1_empty, d2_full, dsig_empty;
+    unsigned long long sigma_ready[kStates][2], fine_ready[kStates], state_free[kStates], omega_ready[2];
+    unsigned int tmem_base, pad1;
+};
+
+struct WsArgs {
+    Geom g;
+    const void* planes;
+    const float *w1, *b1, *w2, *b2;
+    const float *ro, *rd, *u_c, *u_f;
+    const float *ray_t0, *ray_t1;
+    unsigned int* bounds;
+    float *out_rgb, *out_depth, *out_wsum, *out_xyz;
+    long long R;
+    int n_groups, single_pass;
+    int srow, scol, splane;
+    float sigma_cull;
+};
+
+// ------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (int it = 0; it < (1 << 24); ++it) {             // try_wait suspends in hardware; the cap turns a protocol bug into a trap
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    asm volatile("trap;");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+    d |= 1ull << 46;
+    return d;
+}
+__device__ __forceinline__ constexpr uint32_t umma_idesc(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
+    uint32_t r;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r) : "r"(taddr) : "memory");
+    return __uint_as_float(r);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
+    return d;
+}
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    hi = pack_bf16x2(a, b);
+    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+__device__ __forceinline__ void split1(float x, unsigned short& hi, unsigned short& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
+}
+__device__ __forceinline__ int tile_off(int row, int k, int lbo) { return (row >> 3) * kSBO + (k >> 3) * lbo + (row & 7) * 16 + (k & 7) * 2; }
+
+__device__ __forceinline__ void plane_taps32(const Geom& g, const WsArgs& a, int pbase, float ca, float cb, int2* out) {
+    const float gx = __fmul_rn(ca, g.coord_scale), gy = __fmul_rn(cb, g.coord_scale);
+    const float fx = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)g.W), 1.f), 0.5f);
+    const float fy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)g.H), 1.f), 0.5f);
+    const bool sane = (fx > -2.f) && (fx < (float)g.W + 1.f) && (fy > -2.f) && (fy < (float)g.H + 1.f);
+    const float x0f = floorf(fx), y0f = floorf(fy);
+    const float wx1 = fx - x0f, wy1 = fy - y0f;
+    const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    const int x0 = sane ? (int)x0f : -4, y0 = sane ? (int)y0f : -4;
+    const bool vx0 = (unsigned)x0 < (unsigned)g.W, vx1 = (unsigned)(x0 + 1) < (unsigned)g.W;
+    const bool vy0 = (unsigned)y0 < (unsigned)g.H, vy1 = (unsigned)(y0 + 1) < (unsigned)g.H;
+    const int o00 = pbase + y0 * a.srow + x0 * a.scol;
+    int4 lo, hi;
+    lo.x = (vx0 && vy0) ? o00 : 0;                     lo.y = __float_as_int((vx0 && vy0) ? wx0 * wy0 : 0.f);
+    lo.z = (vx1 && vy0) ? o00 + a.scol : 0;            lo.w = __float_as_int((vx1 && vy0) ? wx1 * wy0 : 0.f);
+    hi.x = (vx0 && vy1) ? o00 + a.srow : 0;            hi.y = __float_as_int((vx0 && vy1) ? wx0 * wy1 : 0.f);
+    hi.z = (vx1 && vy1) ? o00 + a.srow + a.scol : 0;   hi.w = __float_as_int((vx1 && vy1) ? wx1 * wy1 : 0.f);
+    reinterpret_cast<int4*>(out)[0] = lo;
+    reinterpret_cast<int4*>(out)[1] = hi;
+}
+template <bool BF16>
+__device__ __forceinline__ float4 load_quad32(const void* qbase, int off) {
+    float4 r;
+    if (BF16) {
+        unsigned int lo, hi;
+        asm("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %3, 2, %2;\n\tld.global.nc.v2.u32 {%0,%1}, [a];\n\t}" : "=r"(lo), "=r"(hi) : "l"(qbase), "r"(off));
+        r = make_float4(__uint_as_float(lo << 16), __uint_as_float(lo & 0xffff0000u), __uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+    } else {
+        asm("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %5, 4, %4;\n\tld.global.nc.v4.f32 {%0,%1,%2,%3}, [a];\n\t}"
+            : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(qbase), "r"(off));
+    }
+    return r;
+}
+
+// position of tile q in the static schedule  C(A) C(B) F(A) F(B) | ...
+struct TileDesc { int n, pass, k; };
+__device__ __forceinline__ TileDesc tile_at(int q) {
+    const int u = q / 12, j = q - u * 12, sub = j / 3;
+    return TileDesc{2 * u + (sub & 1), sub >> 1, j - sub * 3};
+}
+
+// ------------------------------------------------------------------------------------------
+template <bool BF16, int S>
+__global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
+    constexpr int Sf = S, L = 2 * S;
+    constexpr int RPT = S / 3;                   // rows per ray per tile (32 or 16)
+    constexpr int GR = 128 / RPT;                // rays per group (4 or 8)
+    extern __shared__ unsigned char smem_raw[];
+    WsSmem& sm = *reinterpret_cast<WsSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const Geom& g = a.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_my = (a.n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // groups of this CTA
+    const int T = 12 * ((n_my + 1) / 2);
+
+    // ---------------- setup
+    if (warp == kWarpsWS - 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.tmem_base)), "r"(kTmemColsWS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kNA; ++i) { mbar_init(&sm.a1_full[i], kGW); mbar_init(&sm.a1_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.a2_full[i], kEW); mbar_init(&sm.a2_empty[i], 1); mbar_init(&sm.omega_ready[i], kRW); }
+        mbar_init(&sm.d1_full, 1); mbar_init(&sm.d1_empty, kEW); mbar_init(&sm.d2_full, 1); mbar_init(&sm.dsig_empty, 4);
+        for (int i = 0; i < kStates; ++i) {
+            mbar_init(&sm.sigma_ready[i][0], 12); mbar_init(&sm.sigma_ready[i][1], 12);
+            mbar_init(&sm.fine_ready[i], kRW); mbar_init(&sm.state_free[i], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < kHidden * kC; i += kThreadsWS) {            // W1' = W1 * gain * log2(e)   (64 x 32)
+        const int n = i / kC, k = i % kC;
+        unsigned short hi, lo;
+        split1(__fmul_rn(a.w1[i], g.w1_gain) * kLog2e, hi, lo);
+        const int off = tile_off(n, k, kLBO_W1);
+        *reinterpret_cast<unsigned short*>(sm.w1[0] + off) = hi;
+        *reinterpret_cast<unsigned short*>(sm.w1[1] + off) = lo;
+    }
+    for (int i = tid; i < kRgb * kHidden; i += kThreadsWS) {          // colour rows 1..32 of W2, negated   (32 x 64)
+        const int n = i / kHidden, k = i % kHidden;
+        unsigned short hi, lo;
+        split1(-__fmul_rn(a.w2[(n + 1) * kHidden + k], g.w2_gain), hi, lo);
+        const int off = tile_off(n, k, kLBO_W2C);
+        *reinterpret_cast<unsigned short*>(sm.w2c[0] + off) = hi;
+        *reinterpret_cast<unsigned short*>(sm.w2c[1] + off) = lo;
+    }
+    for (int i = tid; i < 16 * kHidden; i += kThreadsWS) {            // sigma row 0 of W2 (* ln2) + 15 zero rows (16 x 64)
+        const int n = i / kHidden, k = i % kHidden;
+        unsigned short hi = 0, lo = 0;
+        if (n == 0) split1(__fmul_rn(a.w2[k], g.w2_gain) * kLn2, hi, lo);
+        const int off = tile_off(n, k, kLBO_W2S);
+        *reinterpret_cast<unsigned short*>(sm.w2s[0] + off) = hi;
+        *reinterpret_cast<unsigned short*>(sm.w2s[1] + off) = lo;
+    }
+    if (tid < kHidden) sm.b1[tid] = __fmul_rn(a.b1[tid], g.b1_gain) * kLog2e;
+    if (tid < kRgb) sm.b2c[tid] = -__fmul_rn(a.b2[tid + 1], g.b2_gain) * kLog2e;
+    if (tid == 0) sm.b2s = __fmul_rn(a.b2[0], g.b2_gain);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = sm.tmem_base;
+
+    if (warp < kGW) {
+        // =========================================================================== GATHER
+        const int gw = warp;
+        int it = 0;
+        for (int q = 0; q < T; ++q) {
+            const TileDesc td = tile_at(q);
+            if (td.n >= n_my) continue;
+            const int grp = (int)blockIdx.x + td.n * (int)gridDim.x;
+            const long long ray0 = (long long)grp * GR;
+            GroupState& st = sm.st[td.n & 3];
+            if (td.k == 0) {
+                if (td.pass == 0) mbar_wait(&sm.state_free[td.n & 3], ((td.n >> 2) & 1) ^ 1);
+                else mbar_wait(&sm.fine_ready[td.n & 3], (td.n >> 2) & 1);
+            }
+            const int stage = it % kNA;
+            mbar_wait(&sm.a1_empty[stage], ((it / kNA) & 1) ^ 1);
+            const int view = (int)(ray0 / g.M);
+            const void* vplanes = BF16 ? (const void*)(reinterpret_cast<const __nv_bfloat16*>(a.planes) + (long long)view * g.stride_view)
+                                       : (const void*)(reinterpret_cast<const float*>(a.planes) + (long long)view * g.stride_view);
+            int2(*taps)[12] = sm.taps[gw];
+            // ---- taps: lane pair per row
+            {
+                const int lrow = lane >> 1, half = lane & 1;
+                const int trow = gw * 16 + lrow;
+                const int rl = trow / RPT, s = td.k * RPT + (trow - rl * RPT);
+                const int srow = rl * S + s;                               // row in the per-group state arrays
+                const long long ray = ray0 + rl;
+                const bool live = ray < a.R;
+                float tval;
+                if (td.pass == 0) {
+                    float u = 0.f;
+                    if (half == 0 && live) {
+                        const long long gidx = ray * S + s;
+                        u = a.u_c ? a.u_c[gidx] : philox_uniform(g.seed, (uint64_t)gidx, 0u);
+                    }
+                    u = __shfl_sync(0xffffffffu, u, lane & ~1);
+                    float t0 = 0.f, t1 = 0.f;
+                    if (g.ray_mode == P3D_RAYS_AUTOBOX && live) {
+                        t0 = a.ray_t0[ray]; t1 = a.ray_t1[ray];
+                        if (!(t1 > t0) && a.bounds[4]) { t0 = ordered_to_float(a.bounds[2]); t1 = ordered_to_float(a.bounds[3]); }
+                    }
+                    tval = coarse_depth(g, s, u, t0, t1);
+                } else {
+                    tval = st.t_f[srow];
+                }
+                float px = 1e30f, py = 1e30f, pz = 1e30f;
+                if (live) {
+                    const float* o = a.ro + ray * 3;
+                    const float* d = a.rd + ray * 3;
+                    px = __fadd_rn(o[0], __fmul_rn(tval, d[0]));
+                    py = __fadd_rn(o[1], __fmul_rn(tval, d[1]));
+                    pz = __fadd_rn(o[2], __fmul_rn(tval, d[2]));
+                }
+                if (half == 0) {
+                    plane_taps32(g, a, 0, px, py, taps[lrow]);
+                    plane_taps32(g, a, a.splane, px, pz, taps[lrow] + 4);
+                } else {
+                    const bool pm = g.plane_mode == P3D_PLANES_PANIC3D;
+                    plane_taps32(g, a, 2 * a.splane, pm ? py : pz, pm ? pz : px, taps[lrow] + 8);
+                    if (td.pass == 0) st.t_c[srow] = tval;
+                    st.crop[td.pass][srow] = (g.crop_on && !((fabsf(px) <= g.crop_limit) && (fabsf(pz) <= g.crop_limit))) ? 1 : 0;
+                }
+            }
+            __syncwarp();
+            // ---- gather: 4 rows per round, 8 lanes per row
+            {
+                const int sub = lane >> 3, qd = lane & 7;
+                const void* qplanes = BF16 ? (const void*)(reinterpret_cast<const __nv_bfloat16*>(vplanes) + 4 * qd)
+                                           : (const void*)(reinterpret_cast<const float*>(vplanes) + 4 * qd);
+                unsigned char* a1h = sm.a1[stage][0];
+                unsigned char* a1l = sm.a1[stage][1];
+#pragma unroll 1
+                for (int round = 0; round < 4; ++round) {
+                    const int lrow = round * 4 + sub;
+                    const int4* tp = reinterpret_cast<const int4*>(taps[lrow]);
+                    int4 tk[6];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) tk[k] = tp[k];
+                    float4 v[12];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        v[2 * k] = load_quad32<BF16>(qplanes, tk[k].x);
+                        v[2 * k + 1] = load_quad32<BF16>(qplanes, tk[k].z);
+                    }
+                    float4 f[3];
+#pragma unroll
+                    for (int p = 0; p < 3; ++p) {
+                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const int4 t2 = tk[2 * p + k];
+                            const float wa = __int_as_float(t2.y), wb = __int_as_float(t2.w);
+                            const float4 va = v[4 * p + 2 * k], vb = v[4 * p + 2 * k + 1];
+                            acc.x = fmaf(va.x, wa, acc.x); acc.y = fmaf(va.y, wa, acc.y); acc.z = fmaf(va.z, wa, acc.z); acc.w = fmaf(va.w, wa, acc.w);
+                            acc.x = fmaf(vb.x, wb, acc.x); acc.y = fmaf(vb.y, wb, acc.y); acc.z = fmaf(vb.z, wb, acc.z); acc.w = fmaf(vb.w, wb, acc.w);
+                        }
+                        f[p] = acc;
+                    }
+                    const float third = 1.f / 3.f;
+                    const float fx = ((f[0].x + f[1].x) + f[2].x) * third, fy = ((f[0].y + f[1].y) + f[2].y) * third;
+                    const float fz = ((f[0].z + f[1].z) + f[2].z) * third, fw = ((f[0].w + f[1].w) + f[2].w) * third;
+                    uint32_t h01, l01, h23, l23;
+                    split2(fx, fy, h01, l01);
+                    split2(fz, fw, h23, l23);
+                    const int off = tile_off(gw * 16 + lrow, 4 * qd, kLBO_A);
+                    *reinterpret_cast<uint2*>(a1h + off) = make_uint2(h01, h23);
+                    *reinterpret_cast<uint2*>(a1l + off) = make_uint2(l01, l23);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.a1_full[stage]);
+            ++it;
+        }
+    } else if (warp < kGW + kEW) {
+        // =========================================================================== EPILOGUE
+        const int e = warp - kGW, quarter = e & 3, chunk = e >> 2;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        const int etid = tid - kGW * 32;                                  // 0..255 inside the epilogue group
+
+        auto sigma_read = [&](int it_prev, const TileDesc& tp) {          // column 0 of the sigma accumulator -> state
+            if (chunk != 0) return;
+            mbar_wait(&sm.d2_full, it_prev & 1);
+            tc_fence_after();
+            float sg = tmem_ld1(tmem + kColSig + lane_base) + sm.b2s;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.dsig_empty);
+            GroupState& st = sm.st[tp.n & 3];
+            const int trow = quarter * 32 + lane;
+            const int rl = trow / RPT, s = tp.k * RPT + (trow - rl * RPT);
+            const int srow = rl * S + s;
+            if (st.crop[tp.pass][srow]) sg = -1e3f;
+            if (g.binarize_on) sg = sg < a.sigma_cull ? -1e3f : 1e3f;
+            else if (g.cull_on && sg < a.sigma_cull) sg = -1e3f;
+            (tp.pass == 0 ? st.sg_c : st.sg_f)[srow] = sg;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.sigma_ready[tp.n & 3][tp.pass]);
+        };
+        auto colours = [&](int n) {                                        // sum_j omega_j * rgb_j for group n, from TMEM
+            const int slot_i = n & 1;
+            SlotState& sl = sm.slot[slot_i];
+            mbar_wait(&sm.omega_ready[slot_i], (n >> 1) & 1);
+            tc_fence_after();
+            const int grp = (int)blockIdx.x + n * (int)gridDim.x;
+            const long long ray0 = (long long)grp * GR;
+            for (int i = 0; i < 3; ++i) {
+                const int tile6 = chunk + 2 * i;                           // this warp's tiles: {0,2,4} or {1,3,5}
+                const int pass = tile6 / 3, k = tile6 - pass * 3;
+                const int trow = quarter * 32 + lane;
+                const int rl = trow / RPT, s = k * RPT + (trow - rl * RPT);
+                const bool live = ray0 + rl < a.R;
+                const float om = live ? sl.om[rl * L + sl.pos[pass * kRowsG + rl * S + s]] : 0.f;
+                const float ca = g.force_sigmoid ? om : 1.002f * om, cb = g.force_sigmoid ? 0.f : -0.001f * om;
+                float v[32];
+                tmem_ld32(tmem + kColD2 + (slot_i * 6 + tile6) * 32 + lane_base, v);
+#pragma unroll
+                for (int c = 0; c < kRgb; ++c) v[c] = fmaf(rcp_approx(1.f + ex2_approx(v[c] + sm.b2c[c])), ca, cb);
+                const int rl_lo = __shfl_sync(0xffffffffu, rl, 0), rl_hi = __shfl_sync(0xffffffffu, rl, 31);
+                for (int target = rl_lo; target <= rl_hi; ++target) {
+                    float r[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) r[c] = (RPT == 32 || rl == target) ? v[c] : 0.f;
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int j = 0; j < off; ++j) {
+                            const float send = up ? r[j] : r[j + off];
+                            const float keep = up ? r[j + off] : r[j];
+                            r[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    atomicAdd(&sl.acc[target][lane], r[0]);
+                }
+            }
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");                 // all eight epilogue warps
+            if (etid < GR * kRgb) {
+                const int rl = etid >> 5, c = etid & 31;
+                const long long ray = ray0 + rl;
+                if (ray < a.R) a.out_rgb[ray * kRgb + c] = __fsub_rn(__fmul_rn(__fadd_rn(sl.acc[rl][c], sl.back[rl]), 2.f), 1.f);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (etid == 0) mbar_arrive(&sm.state_free[n & 3]);
+        };
+
+        int it = 0;
+        TileDesc prev{0, 0, 0};
+        bool have_prev = false;
+        for (int q = 0; q < T; ++q) {
+            const TileDesc td = tile_at(q);
+            if (td.n >= n_my) continue;
+            if (td.pass == 0 && td.k == 0 && td.n >= 2) colours(td.n - 2);   // frees the TMEM slot this group is about to reuse
+            // ---- epilogue 1: D1 -> softplus2 -> A2[buf]
+            mbar_wait(&sm.d1_full, it & 1);
+            tc_fence_after();
+            float v[32];
+            tmem_ld32(tmem + kColD1 + lane_base + 32 * chunk, v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.d1_empty);
+            const int buf = it & 1;
+            mbar_wait(&sm.a2_empty[buf], ((it >> 1) & 1) ^ 1);
+            {
+                const int trow = quarter * 32 + lane;
+                unsigned char* a2h = sm.a2[buf][0];
+                unsigned char* a2l = sm.a2[buf][1];
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    uint32_t ph[4], pl[4];
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        const int j = c8 * 8 + 2 * x;
+                        split2(softplus2(v[j] + sm.b1[32 * chunk + j]), softplus2(v[j + 1] + sm.b1[32 * chunk + j + 1]), ph[x], pl[x]);
+                    }
+                    const int off = tile_off(trow, 32 * chunk + 8 * c8, kLBO_A);
+                    *reinterpret_cast<uint4*>(a2h + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                    *reinterpret_cast<uint4*>(a2l + off) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.a2_full[buf]);
+            // ---- sigma of the PREVIOUS tile (its layer 2 has had a whole epilogue to finish)
+            if (have_prev) sigma_read(it - 1, prev);
+            prev = td; have_prev = true;
+            ++it;
+            // odd tail: the next tile (F of the same, last group) waits on THIS tile's sigma -> do not defer it
+            if ((n_my & 1) && td.n == n_my - 1 && td.pass == 0 && td.k == 2) { sigma_read(it - 1, prev); have_prev = false; }
+        }
+        if (have_prev) sigma_read(it - 1, prev);
+        for (int n = (n_my >= 2 ? n_my - 2 : 0); n < n_my; ++n) colours(n);
+    } else if (warp < kGW + kEW + kRW) {
+        // =========================================================================== RAYS
+        const int rw = warp - kGW - kEW;
+        float* scr = sm.rscratch[rw];
+        for (int u = 0; u * 2 < n_my; ++u) {
+            for (int phase = 0; phase < 4; ++phase) {                      // imp(A) imp(B) comp(A) comp(B)
+                const int n = 2 * u + (phase & 1);
+                if (n >= n_my) continue;
+                const int pass = phase >> 1;
+                GroupState& st = sm.st[n & 3];
+                SlotState& sl = sm.slot[n & 1];
+                const int grp = (int)blockIdx.x + n * (int)gridDim.x;
+                const long long ray0 = (long long)grp * GR;
+                mbar_wait(&sm.sigma_ready[n & 3][pass], (n >> 2) & 1);
+                if (pass == 0) {
+                    // ---------------- importance sampling, one ray at a time (renderer.py:328-387)
+                    for (int rl = rw; rl < GR; rl += kRW) {
+                        const long long ray = ray0 + rl;
+                        const float* t = st.t_c + rl * S;
+                        const float* sg = st.sg_c + rl * S;
+                        float* w = scr;                 // [S]
+                        float* cdf = scr + S;           // [S]
+                        float* tfu = scr + 2 * S;       // [S] unsorted
+                        constexpr int nb = S - 3;
+                        float carry = 1.f;
+#pragma unroll
+                        for (int c = 0; c < (S + 31) / 32; ++c) {
+                            const int i = c * 32 + lane;
+                            float alpha = 0.f, fac = 1.f;
+                            if (i < S - 1) {
+                                const float smid = __fsub_rn(__fmul_rn(__fadd_rn(sg[i], sg[i + 1]), 0.5f), 1.f);
+                                alpha = 1.f - ex2_approx(-kLog2e * __fmul_rn(softplus_mufu(smid), t[i + 1] - t[i]));
+                                fac = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+                            }
+                            const float incl = warp_scan_mul(fac, lane);
+                            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                            if (lane == 0) excl = 1.f;
+                            if (i < S - 1) w[i] = alpha * (carry * excl);
+                            carry *= __shfl_sync(0xffffffffu, incl, 31);
+                        }
+                        __syncwarp();
+                        float my[(S + 31) / 32];
+                        float part = 0.f;
+#pragma unroll
+                        for (int c = 0; c < (S + 31) / 32; ++c) {
+                            const int k = c * 32 + lane;
+                            float v = 0.f;
+                            if (k < nb) v = __fadd_rn(__fadd_rn(__fmul_rn(__fadd_rn(fmaxf(w[k], w[k + 1]), fmaxf(w[k + 1], w[k + 2])), 0.5f), 0.01f), 1e-5f);
+                            my[c] = v; part += v;
+                        }
+                        const float total = warp_sum(part);
+                        float csum = 0.f;
+#pragma unroll
+                        for (int c = 0; c < (S + 31) / 32; ++c) {
+                            const int k = c * 32 + lane;
+                            const float incl = warp_scan_add(k < nb ? __fdiv_rn(my[c], total) : 0.f, lane) + csum;
+                            if (k < nb) cdf[k + 1] = incl;
+                            csum = __shfl_sync(0xffffffffu, incl, 31);
+                        }
+                        if (lane == 0) cdf[0] = 0.f;
+                        __syncwarp();
+                        for (int f = lane; f < Sf; f += 32) {
+                            float val = INFINITY;
+                            if (ray < a.R) {
+                                const float u = a.u_f ? a.u_f[ray * Sf + f] : philox_uniform(g.seed, (uint64_t)(ray * Sf + f), 1u);
+                                int lo = 0, hi = nb + 1;
+                                while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+                                const int below = max(lo - 1, 0), above = min(lo, nb);
+                                const float c0 = cdf[below], c1 = cdf[above];
+                                const float b0 = __fmul_rn(0.5f, __fadd_rn(t[below], t[below + 1]));
+                                const float b1 = __fmul_rn(0.5f, __fadd_rn(t[above], t[above + 1]));
+                                float den = __fsub_rn(c1, c0);
+                                if (den < 1e-5f) den = 1.f;
+                                val = __fadd_rn(b0, __fmul_rn(__fdiv_rn(__fsub_rn(u, c0), den), __fsub_rn(b1, b0)));
+                            }
+                            tfu[f] = val;
+                        }
+                        __syncwarp();
+                        for (int j = lane; j < Sf; j += 32) {              // stable rank sort
+                            const float tj = tfu[j];
+                            const float4* row = reinterpret_cast<const float4*>(tfu);
+                            int rank = 0;
+#pragma unroll 4
+                            for (int k4 = 0; k4 < S / 4; ++k4) {
+                                const float4 t4 = row[k4];
+                                const int k = 4 * k4;
+                                rank += (t4.x < tj || (t4.x == tj && k + 0 < j)) + (t4.y < tj || (t4.y == tj && k + 1 < j)) +
+                                        (t4.z < tj || (t4.z == tj && k + 2 < j)) + (t4.w < tj || (t4.w == tj && k + 3 < j));
+                            }
+                            st.t_f[rl * Sf + rank] = tj;
+                        }
+                        __syncwarp();
+                    }
+                    if (lane == 0) mbar_arrive(&sm.fine_ready[n & 3]);
+                } else {
+                    // ---------------- merge + transmittance + omega (renderer.py:289-301, ray_marcher.py:25-44)
+                    for (int rl = rw; rl < GR; rl += kRW) {
+                        const long long ray = ray0 + rl;
+                        const float* tc = st.t_c + rl * S;
+                        const float* tf = st.t_f + rl * Sf;
+                        float* m_t = scr;               // [L]
+                        float* m_sg = scr + L;          // [L]
+                        float* m_al = scr + 2 * L;      // [L]
+                        float* m_fc = scr + 3 * L;      // [L]
+                        const bool rev = tc[0] > tc[S - 1];
+                        for (int i = lane; i < S; i += 32) {
+                            const int ci = rev ? S - 1 - i : i;
+                            const float tv = tc[ci];
+                            int lo = 0, hi = Sf;
+                            while (lo < hi) { const int mid = (lo + hi) >> 1; if (tf[mid] < tv) lo = mid + 1; else hi = mid; }
+                            const int pos = i + lo;
+                            m_t[pos] = tv; m_sg[pos] = st.sg_c[rl * S + ci]; sl.pos[rl * S + ci] = pos;
+                        }
+                        for (int j = lane; j < Sf; j += 32) {
+                            const float tv = tf[j];
+                            int lo = 0, hi = S;
+                            while (lo < hi) { const int mid = (lo + hi) >> 1; if (tc[rev ? S - 1 - mid : mid] <= tv) lo = mid + 1; else hi = mid; }
+                            const int pos = j + lo;
+                            m_t[pos] = tv; m_sg[pos] = st.sg_f[rl * Sf + j]; sl.pos[kRowsG + rl * Sf + j] = pos;
+                        }
+                        __syncwarp();
+                        for (int i = lane; i < L; i += 32) {
+                            float alpha = 0.f, fac = 1.f;
+                            if (i < L - 1) {
+                                const float smid = __fsub_rn(__fmul_rn(__fadd_rn(m_sg[i], m_sg[i + 1]), 0.5f), 1.f);
+                                alpha = 1.f - ex2_approx(-kLog2e * __fmul_rn(softplus_mufu(smid), m_t[i + 1] - m_t[i]));
+                                fac = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+                            }
+                            m_al[i] = alpha; m_fc[i] = fac;
+                        }
+                        __syncwarp();
+                        float carry = 1.f, acc_w = 0.f, acc_d = 0.f, wprev = 0.f;
+#pragma unroll
+                        for (int c = 0; c < L / 32; ++c) {
+                            const int i = c * 32 + lane;
+                            const float incl = warp_scan_mul(m_fc[i], lane);
+                            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                            if (lane == 0) excl = 1.f;
+                            const float wi = m_al[i] * (carry * excl);
+                            carry *= __shfl_sync(0xffffffffu, incl, 31);
+                            acc_w += wi;
+                            if (i < L - 1) acc_d = fmaf(wi, __fmul_rn(__fadd_rn(m_t[i], m_t[i + 1]), 0.5f), acc_d);
+                            float wl = __shfl_up_sync(0xffffffffu, wi, 1);
+                            if (lane == 0) wl = wprev;
+                            wprev = __shfl_sync(0xffffffffu, wi, 31);
+                            sl.om[rl * L + i] = __fmul_rn(__fadd_rn(wl, wi), 0.5f);
+                        }
+                        const float wsum = warp_sum(acc_w), dnum = warp_sum(acc_d);
+                        const float back = g.white_back ? __fsub_rn(1.f, wsum) : 0.f;
+                        sl.acc[rl][lane] = 0.f;
+                        if (ray < a.R) {
+                            if (lane < 3) {
+                                const float v = fmaf(a.ro[ray * 3 + lane], wsum, a.rd[ray * 3 + lane] * dnum);
+                                a.out_xyz[ray * 3 + lane] = __fsub_rn(__fmul_rn(__fadd_rn(v, back), 2.f), 1.f);
+                            }
+                            if (lane == 0) {
+                                a.out_depth[ray] = __fdiv_rn(dnum, wsum);
+                                a.out_wsum[ray] = wsum;
+                                atomicMin(&a.bounds[0], float_to_ordered(m_t[0]));
+                                atomicMax(&a.bounds[1], float_to_ordered(m_t[L - 1]));
+                            }
+                        }
+                        if (lane == 0) sl.back[rl] = back;
+                        __syncwarp();
+                    }
+                    if (lane == 0) mbar_arrive(&sm.omega_ready[n & 1]);
+                }
+            }
+        }
+    } else {
+        // =========================================================================== MMA issuer (one thread)
+        if (lane == 0) {
+            const uint32_t idesc1 = umma_idesc(128, kHidden), idesc2c = umma_idesc(128, kRgb), idesc2s = umma_idesc(128, 16);
+            const uint32_t w1h = smem_u32(sm.w1[0]), w1l = smem_u32(sm.w1[1]);
+            const uint32_t w2ch = smem_u32(sm.w2c[0]), w2cl = smem_u32(sm.w2c[1]), w2sh = smem_u32(sm.w2s[0]), w2sl = smem_u32(sm.w2s[1]);
+            auto layer2 = [&](int it2, const TileDesc& tp) {
+                const int buf = it2 & 1;
+                mbar_wait(&sm.a2_full[buf], (it2 >> 1) & 1);
+                mbar_wait(&sm.dsig_empty, (it2 & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t a2h = smem_u32(sm.a2[buf][0]), a2l = smem_u32(sm.a2[buf][1]);
+                const uint32_t dc = tmem + kColD2 + ((tp.n & 1) * 6 + tp.pass * 3 + tp.k) * 32, ds = tmem + kColSig;
+#pragma unroll
+                for (int ks = 0; ks < kHidden / 16; ++ks) {
+                    const uint32_t ao = ks * 2 * kLBO_A;
+                    umma_bf16(dc, umma_desc(a2h + ao, kLBO_A, kSBO), umma_desc(w2ch + ks * 2 * kLBO_W2C, kLBO_W2C, kSBO), idesc2c, ks > 0);
+                    umma_bf16(ds, umma_desc(a2h + ao, kLBO_A, kSBO), umma_desc(w2sh + ks * 2 * kLBO_W2S, kLBO_W2S, kSBO), idesc2s, ks > 0);
+                    if (!a.single_pass) {
+                        umma_bf16(dc, umma_desc(a2h + ao, kLBO_A, kSBO), umma_desc(w2cl + ks * 2 * kLBO_W2C, kLBO_W2C, kSBO), idesc2c, 1);
+                        umma_bf16(dc, umma_desc(a2l + ao, kLBO_A, kSBO), umma_desc(w2ch + ks * 2 * kLBO_W2C, kLBO_W2C, kSBO), idesc2c, 1);
+                        umma_bf16(ds, umma_desc(a2h + ao, kLBO_A, kSBO), umma_desc(w2sl + ks * 2 * kLBO_W2S, kLBO_W2S, kSBO), idesc2s, 1);
+                        umma_bf16(ds, umma_desc(a2l + ao, kLBO_A, kSBO), umma_desc(w2sh + ks * 2 * kLBO_W2S, kLBO_W2S, kSBO), idesc2s, 1);
+                    }
+                }
+                umma_commit(&sm.d2_full);
+                umma_commit(&sm.a2_empty[buf]);
+            };
+            int it = 0;
+            TileDesc prev{0, 0, 0};
+            bool have_prev = false;
+            for (int q = 0; q < T; ++q) {
+                const TileDesc td = tile_at(q);
+                if (td.n >= n_my) continue;
+                const int stage = it % kNA;
+                mbar_wait(&sm.a1_full[stage], (it / kNA) & 1);
+                mbar_wait(&sm.d1_empty, (it & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t a1h = smem_u32(sm.a1[stage][0]), a1l = smem_u32(sm.a1[stage][1]);
+#pragma unroll
+                for (int ks = 0; ks < kC / 16; ++ks) {
+                    const uint32_t ao = ks * 2 * kLBO_A, bo = ks * 2 * kLBO_W1;
+                    umma_bf16(tmem + kColD1, umma_desc(a1h + ao, kLBO_A, kSBO), umma_desc(w1h + bo, kLBO_W1, kSBO), idesc1, ks > 0);
+                    if (!a.single_pass) {
+                        umma_bf16(tmem + kColD1, umma_desc(a1h + ao, kLBO_A, kSBO), umma_desc(w1l + bo, kLBO_W1, kSBO), idesc1, 1);
+                        umma_bf16(tmem + kColD1, umma_desc(a1l + ao, kLBO_A, kSBO), umma_desc(w1h + bo, kLBO_W1, kSBO), idesc1, 1);
+                    }
+                }
+                umma_commit(&sm.d1_full);
+                umma_commit(&sm.a1_empty[stage]);
+                if (have_prev) layer2(it - 1, prev);
+                prev = td; have_prev = true;
+                ++it;
+                if ((n_my & 1) && td.n == n_my - 1 && td.pass == 0 && td.k == 2) { layer2(it - 1, prev); have_prev = false; }   // see EPILOGUE
+            }
+            if (have_prev) layer2(it - 1, prev);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWarpsWS - 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kTmemColsWS) : "memory");
+    }
+}
+
+}  // namespace
+
+int launch_bounds_init(unsigned int* bounds, cudaStream_t stream);
+int launch_ray_limits(const float* ro, const float* rd, long long R, float h, float* t0, float* t1, unsigned int* bounds, cudaStream_t stream);
+int launch_depth_finalize(float* depth, long long R, const unsigned int* bounds, cudaStream_t stream);
+
+bool fused_ws_supported(const Geom& g) {
+    if (!((g.S == 96 || g.S == 48) && (g.Sf == g.S) && ((long long)g.M % (384 / g.S) == 0))) return false;
+    const long long span = 2 * g.stride_plane + (long long)(g.H - 1) * g.stride_row + (long long)(g.W - 1) * g.stride_col + kC;
+    return g.stride_plane >= 0 && g.stride_row >= 0 && g.stride_col >= 0 && span < (1ll << 31);
+}
+
+int render_forward_fused_ws(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
+                            const float* w2, const float* b2, const float* ro, const float* rd, const float* u_c,
+                            const float* u_f, const Workspace& ws, float* out_rgb, float* out_depth, float* out_wsum,
+                            float* out_xyz, cudaStream_t stream) {
+    if (!fused_ws_supported(g)) {
+        set_error("warp-specialised renderer supports depth_resolution == depth_resolution_importance in {48, 96} (got %d, %d)", g.S, g.Sf);
+        return P3D_EUNSUPPORTED;
+    }
+    const long long R = (long long)g.N * g.M;
+    int rc;
+    if ((rc = launch_bounds_init(ws.bounds, stream))) return rc;
+    if (g.ray_mode == P3D_RAYS_AUTOBOX)
+        if ((rc = launch_ray_limits(ro, rd, R, g.half_box, ws.ray_t0, ws.ray_t1, ws.bounds, stream))) return rc;
+    WsArgs a{};
+    a.g = g; a.planes = planes; a.w1 = w1; a.b1 = b1; a.w2 = w2; a.b2 = b2; a.ro = ro; a.rd = rd; a.u_c = u_c; a.u_f = u_f;
+    a.ray_t0 = ws.ray_t0; a.ray_t1 = ws.ray_t1; a.bounds = ws.bounds;
+    a.out_rgb = out_rgb; a.out_depth = out_depth; a.out_wsum = out_wsum; a.out_xyz = out_xyz;
+    const int GR = 384 / g.S;
+    a.R = R; a.n_groups = (int)((R + GR - 1) / GR);
+    a.single_pass = p->mlp_mode == P3D_MLP_TC_BF16;
+    a.srow = (int)g.stride_row; a.scol = (int)g.stride_col; a.splane = (int)g.stride_plane;
+    if (g.cull_on || g.binarize_on) {
+        const double thr = (double)g.cull_thresh;
+        a.sigma_cull = thr >= 1.0 ? INFINITY : (thr <= 0.0 ? -INFINITY : (float)(1.0 + log(expm1(-log1p(-thr)))));
+    }
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        P3D_CUDA_TRY(cudaGetDevice(&dev));
+        P3D_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const size_t smem = sizeof(WsSmem) + 1024;
+    void (*kern)(WsArgs) = nullptr;
+    if (g.S == 96) kern = p->planes_bf16 ? k_render_ws<true, 96> : k_render_ws<false, 96>;
+    else kern = p->planes_bf16 ? k_render_ws<true, 48> : k_render_ws<false, 48>;
+    P3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = a.n_groups < n_sm ? a.n_groups : n_sm;
+    {
+        ProfileScope prof(PROF_FUSED, stream);
+        kern<<<grid, kThreadsWS, smem, stream>>>(a);
+        P3D_LAUNCH_CHECK();
+    }
+    if (p->defer_depth_clamp) return P3D_OK;
+    return launch_depth_finalize(out_depth, R, ws.bounds, stream);
+}
+
+}  // namespace p3d
