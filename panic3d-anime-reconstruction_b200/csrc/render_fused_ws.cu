@@ -1,11 +1,12 @@
-// Warp-specialised fused renderer (v3): one persistent CTA per SM, 19 warps in four roles, two ray groups in
+// Warp-specialised fused renderer (v3): one persistent CTA per SM, 21 warps in three roles, two ray groups in
 // flight, every hand-off through mbarriers.
 //
-//   warps  0- 7  GATHER    per tile: 16 rows each; taps -> 12 x 128-bit loads per lane -> lerp -> bf16 hi/lo A1 tile
-//   warps  8-15  EPILOGUE  per tile: tcgen05.ld D1 -> softplus2 -> A2 tile; sigma read-back; at group end the
-//                          colour reduction straight out of TMEM
-//   warps 16-17  RAYS      per group: importance sampling after the coarse pass, merge/transmittance after the fine
-//   warp  18     MMA       one thread: layer-1 (N=64) and layer-2 (N=32 colour + N=16 sigma) tcgen05.mma, commits
+//   warps  0-11  GATHER    three teams of four warps; team j takes tiles j, j+3, ... of the tile sequence; a warp owns
+//                          32 rows of its tile: taps -> 12 x 128-bit loads per lane -> lerp -> bf16 hi/lo A1 tile
+//   warps 12-19  EPILOGUE  per tile: tcgen05.ld D1 -> softplus2 -> A2 tile; sigma read-back; after a group's coarse
+//                          pass the importance sampling, after its fine pass merge/transmittance and the colour
+//                          reduction straight out of TMEM (256 threads, named barrier 1)
+//   warp  20     MMA       one thread: layer-1 (N=64) and layer-2 (N=32 colour + N=16 sigma) tcgen05.mma, commits
 //
 // A ray group is 384/S rays (4 at S=Sf=96, 8 at 48); a pass over it is three full 128-row tiles, tile k holding
 // samples [k*S/3, (k+1)*S/3) of every ray, so a TMEM lane quarter is one ray's 32 consecutive samples.
@@ -21,10 +22,10 @@ namespace {
 
 using namespace dev;
 
-constexpr int kGW = 8, kEW = 8, kRW = 2;
-constexpr int kWarpsWS = kGW + kEW + kRW + 1;
-constexpr int kThreadsWS = kWarpsWS * 32;        // 608
-constexpr int kNA = 3;                           // A1 ring depth
+constexpr int kGW = 12, kEW = 8, kTeams = 3;
+constexpr int kWarpsWS = kGW + kEW + 1;
+constexpr int kThreadsWS = kWarpsWS * 32;        // 672
+constexpr int kNA = 4;                           // A1 ring depth
 constexpr int kStates = 4;                       // per-group state ring
 constexpr int kRowsG = 384;                      // rows per pass per group
 constexpr int kTmemColsWS = 512;
@@ -49,13 +50,13 @@ struct __align__(1024) WsSmem {
     unsigned char a2[2][2][16384];
     unsigned char w1[2][4096], w2c[2][4096], w2s[2][2048];
     float b1[kHidden], b2c[kRgb], b2s, pad0[3];
-    int2 taps[kGW][16][12];
+    int2 taps[kGW][16][12];                       // 16 rows at a time per gather warp
     GroupState st[kStates];
     SlotState slot[2];
-    float rscratch[kRW][1536];
+    float rscratch[3072];                          // per-ray phases of the epilogue group (importance / merge)
     unsigned long long a1_full[kNA], a1_empty[kNA], a2_full[2], a2_empty[2];
     unsigned long long d1_full, d1_empty, d2_full, dsig_empty;
-    unsigned long long sigma_ready[kStates][2], fine_ready[kStates], state_free[kStates], omega_ready[2];
+    unsigned long long fine_ready[kStates], state_free[kStates];
     unsigned int tmem_base, pad1;
 };
 
@@ -206,13 +207,10 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        for (int i = 0; i < kNA; ++i) { mbar_init(&sm.a1_full[i], kGW); mbar_init(&sm.a1_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&sm.a2_full[i], kEW); mbar_init(&sm.a2_empty[i], 1); mbar_init(&sm.omega_ready[i], kRW); }
+        for (int i = 0; i < kNA; ++i) { mbar_init(&sm.a1_full[i], 4); mbar_init(&sm.a1_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&sm.a2_full[i], kEW); mbar_init(&sm.a2_empty[i], 1); }
         mbar_init(&sm.d1_full, 1); mbar_init(&sm.d1_empty, kEW); mbar_init(&sm.d2_full, 1); mbar_init(&sm.dsig_empty, 4);
-        for (int i = 0; i < kStates; ++i) {
-            mbar_init(&sm.sigma_ready[i][0], 12); mbar_init(&sm.sigma_ready[i][1], 12);
-            mbar_init(&sm.fine_ready[i], kRW); mbar_init(&sm.state_free[i], 1);
-        }
+        for (int i = 0; i < kStates; ++i) { mbar_init(&sm.fine_ready[i], 1); mbar_init(&sm.state_free[i], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < kHidden * kC; i += kThreadsWS) {            // W1' = W1 * gain * log2(e)   (64 x 32)
@@ -250,75 +248,77 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
 
     if (warp < kGW) {
         // =========================================================================== GATHER
-        const int gw = warp;
+        const int gw = warp, team = gw >> 2, wt = gw & 3;
         int it = 0;
         for (int q = 0; q < T; ++q) {
             const TileDesc td = tile_at(q);
             if (td.n >= n_my) continue;
+            const int my_it = it++;
+            if (my_it % kTeams != team) continue;
             const int grp = (int)blockIdx.x + td.n * (int)gridDim.x;
             const long long ray0 = (long long)grp * GR;
             GroupState& st = sm.st[td.n & 3];
-            if (td.k == 0) {
-                if (td.pass == 0) mbar_wait(&sm.state_free[td.n & 3], ((td.n >> 2) & 1) ^ 1);
-                else mbar_wait(&sm.fine_ready[td.n & 3], (td.n >> 2) & 1);
-            }
-            const int stage = it % kNA;
-            mbar_wait(&sm.a1_empty[stage], ((it / kNA) & 1) ^ 1);
+            if (td.pass == 0) mbar_wait(&sm.state_free[td.n & 3], ((td.n >> 2) & 1) ^ 1);
+            else mbar_wait(&sm.fine_ready[td.n & 3], (td.n >> 2) & 1);
+            const int stage = my_it % kNA;
+            mbar_wait(&sm.a1_empty[stage], ((my_it / kNA) & 1) ^ 1);
             const int view = (int)(ray0 / g.M);
             const void* vplanes = BF16 ? (const void*)(reinterpret_cast<const __nv_bfloat16*>(a.planes) + (long long)view * g.stride_view)
                                        : (const void*)(reinterpret_cast<const float*>(a.planes) + (long long)view * g.stride_view);
             int2(*taps)[12] = sm.taps[gw];
-            // ---- taps: lane pair per row
-            {
-                const int lrow = lane >> 1, half = lane & 1;
-                const int trow = gw * 16 + lrow;
-                const int rl = trow / RPT, s = td.k * RPT + (trow - rl * RPT);
-                const int srow = rl * S + s;                               // row in the per-group state arrays
-                const long long ray = ray0 + rl;
-                const bool live = ray < a.R;
-                float tval;
-                if (td.pass == 0) {
-                    float u = 0.f;
-                    if (half == 0 && live) {
-                        const long long gidx = ray * S + s;
-                        u = a.u_c ? a.u_c[gidx] : philox_uniform(g.seed, (uint64_t)gidx, 0u);
+            const int sub = lane >> 3, qd = lane & 7;
+            const void* qplanes = BF16 ? (const void*)(reinterpret_cast<const __nv_bfloat16*>(vplanes) + 4 * qd)
+                                       : (const void*)(reinterpret_cast<const float*>(vplanes) + 4 * qd);
+            unsigned char* a1h = sm.a1[stage][0];
+            unsigned char* a1l = sm.a1[stage][1];
+#pragma unroll 1
+            for (int half_tile = 0; half_tile < 2; ++half_tile) {
+                const int row0 = wt * 32 + half_tile * 16;                 // this warp's 16 rows of the tile
+                // ---- taps: lane pair per row
+                {
+                    const int lrow = lane >> 1, half = lane & 1;
+                    const int trow = row0 + lrow;
+                    const int rl = trow / RPT, s = td.k * RPT + (trow - rl * RPT);
+                    const int srow = rl * S + s;                           // row in the per-group state arrays
+                    const long long ray = ray0 + rl;
+                    const bool live = ray < a.R;
+                    float tval;
+                    if (td.pass == 0) {
+                        float u = 0.f;
+                        if (half == 0 && live) {
+                            const long long gidx = ray * S + s;
+                            u = a.u_c ? a.u_c[gidx] : philox_uniform(g.seed, (uint64_t)gidx, 0u);
+                        }
+                        u = __shfl_sync(0xffffffffu, u, lane & ~1);
+                        float t0 = 0.f, t1 = 0.f;
+                        if (g.ray_mode == P3D_RAYS_AUTOBOX && live) {
+                            t0 = a.ray_t0[ray]; t1 = a.ray_t1[ray];
+                            if (!(t1 > t0) && a.bounds[4]) { t0 = ordered_to_float(a.bounds[2]); t1 = ordered_to_float(a.bounds[3]); }
+                        }
+                        tval = coarse_depth(g, s, u, t0, t1);
+                    } else {
+                        tval = st.t_f[srow];
                     }
-                    u = __shfl_sync(0xffffffffu, u, lane & ~1);
-                    float t0 = 0.f, t1 = 0.f;
-                    if (g.ray_mode == P3D_RAYS_AUTOBOX && live) {
-                        t0 = a.ray_t0[ray]; t1 = a.ray_t1[ray];
-                        if (!(t1 > t0) && a.bounds[4]) { t0 = ordered_to_float(a.bounds[2]); t1 = ordered_to_float(a.bounds[3]); }
+                    float px = 1e30f, py = 1e30f, pz = 1e30f;
+                    if (live) {
+                        const float* o = a.ro + ray * 3;
+                        const float* d = a.rd + ray * 3;
+                        px = __fadd_rn(o[0], __fmul_rn(tval, d[0]));
+                        py = __fadd_rn(o[1], __fmul_rn(tval, d[1]));
+                        pz = __fadd_rn(o[2], __fmul_rn(tval, d[2]));
                     }
-                    tval = coarse_depth(g, s, u, t0, t1);
-                } else {
-                    tval = st.t_f[srow];
+                    if (half == 0) {
+                        plane_taps32(g, a, 0, px, py, taps[lrow]);
+                        plane_taps32(g, a, a.splane, px, pz, taps[lrow] + 4);
+                    } else {
+                        const bool pm = g.plane_mode == P3D_PLANES_PANIC3D;
+                        plane_taps32(g, a, 2 * a.splane, pm ? py : pz, pm ? pz : px, taps[lrow] + 8);
+                        if (td.pass == 0) st.t_c[srow] = tval;
+                        st.crop[td.pass][srow] = (g.crop_on && !((fabsf(px) <= g.crop_limit) && (fabsf(pz) <= g.crop_limit))) ? 1 : 0;
+                    }
                 }
-                float px = 1e30f, py = 1e30f, pz = 1e30f;
-                if (live) {
-                    const float* o = a.ro + ray * 3;
-                    const float* d = a.rd + ray * 3;
-                    px = __fadd_rn(o[0], __fmul_rn(tval, d[0]));
-                    py = __fadd_rn(o[1], __fmul_rn(tval, d[1]));
-                    pz = __fadd_rn(o[2], __fmul_rn(tval, d[2]));
-                }
-                if (half == 0) {
-                    plane_taps32(g, a, 0, px, py, taps[lrow]);
-                    plane_taps32(g, a, a.splane, px, pz, taps[lrow] + 4);
-                } else {
-                    const bool pm = g.plane_mode == P3D_PLANES_PANIC3D;
-                    plane_taps32(g, a, 2 * a.splane, pm ? py : pz, pm ? pz : px, taps[lrow] + 8);
-                    if (td.pass == 0) st.t_c[srow] = tval;
-                    st.crop[td.pass][srow] = (g.crop_on && !((fabsf(px) <= g.crop_limit) && (fabsf(pz) <= g.crop_limit))) ? 1 : 0;
-                }
-            }
-            __syncwarp();
-            // ---- gather: 4 rows per round, 8 lanes per row
-            {
-                const int sub = lane >> 3, qd = lane & 7;
-                const void* qplanes = BF16 ? (const void*)(reinterpret_cast<const __nv_bfloat16*>(vplanes) + 4 * qd)
-                                           : (const void*)(reinterpret_cast<const float*>(vplanes) + 4 * qd);
-                unsigned char* a1h = sm.a1[stage][0];
-                unsigned char* a1l = sm.a1[stage][1];
+                __syncwarp();
+                // ---- gather: 4 rows per round, 8 lanes per row
 #pragma unroll 1
                 for (int round = 0; round < 4; ++round) {
                     const int lrow = round * 4 + sub;
@@ -352,15 +352,15 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
                     uint32_t h01, l01, h23, l23;
                     split2(fx, fy, h01, l01);
                     split2(fz, fw, h23, l23);
-                    const int off = tile_off(gw * 16 + lrow, 4 * qd, kLBO_A);
+                    const int off = tile_off(row0 + lrow, 4 * qd, kLBO_A);
                     *reinterpret_cast<uint2*>(a1h + off) = make_uint2(h01, h23);
                     *reinterpret_cast<uint2*>(a1l + off) = make_uint2(l01, l23);
                 }
+                __syncwarp();                                               // taps buffer is reused by the next half
             }
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.a1_full[stage]);
-            ++it;
         }
     } else if (warp < kGW + kEW) {
         // =========================================================================== EPILOGUE
@@ -384,13 +384,191 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             if (g.binarize_on) sg = sg < a.sigma_cull ? -1e3f : 1e3f;
             else if (g.cull_on && sg < a.sigma_cull) sg = -1e3f;
             (tp.pass == 0 ? st.sg_c : st.sg_f)[srow] = sg;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.sigma_ready[tp.n & 3][tp.pass]);
+        };
+        auto ebar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };   // the eight epilogue warps
+        // ---- importance sampling for group n (renderer.py:328-387), 256 threads
+        auto importance = [&](int n) {
+            GroupState& st = sm.st[n & 3];
+            const int grp = (int)blockIdx.x + n * (int)gridDim.x;
+            const long long ray0 = (long long)grp * GR;
+            float* i_alpha = sm.rscratch;            // [384]
+            float* i_fac = sm.rscratch + 384;        // [384]
+            float* i_w = sm.rscratch + 768;          // [384]
+            float* i_cdf = sm.rscratch + 1152;       // [384]
+            float* i_tfu = sm.rscratch + 1536;       // [384]
+            constexpr int nb = S - 3;
+            ebar();                                   // sigma of the last coarse tile is in shared memory
+            for (int r = etid; r < kRowsG; r += 256) {
+                const int i = r % S;
+                float alpha = 0.f, fac = 1.f;
+                if (i < S - 1) {
+                    const float smid = __fsub_rn(__fmul_rn(__fadd_rn(st.sg_c[r], st.sg_c[r + 1]), 0.5f), 1.f);
+                    alpha = 1.f - ex2_approx(-kLog2e * __fmul_rn(softplus_mufu(smid), st.t_c[r + 1] - st.t_c[r]));
+                    fac = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+                }
+                i_alpha[r] = alpha; i_fac[r] = fac;
+            }
+            ebar();
+            for (int rl = e; rl < GR; rl += kEW) {   // warp per ray: transmittance scan -> weights -> pooled pdf -> cdf
+                float carry = 1.f;
+#pragma unroll
+                for (int c = 0; c < (S + 31) / 32; ++c) {
+                    const int i = c * 32 + lane;
+                    const float f = i < S - 1 ? i_fac[rl * S + i] : 1.f;
+                    const float incl = warp_scan_mul(f, lane);
+                    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                    if (lane == 0) excl = 1.f;
+                    if (i < S - 1) i_w[rl * S + i] = i_alpha[rl * S + i] * (carry * excl);
+                    carry *= __shfl_sync(0xffffffffu, incl, 31);
+                }
+                __syncwarp();
+                float my[(S + 31) / 32];
+                float part = 0.f;
+#pragma unroll
+                for (int c = 0; c < (S + 31) / 32; ++c) {
+                    const int k = c * 32 + lane;
+                    float v = 0.f;
+                    if (k < nb) {
+                        const float* w = i_w + rl * S + k;
+                        v = __fadd_rn(__fadd_rn(__fmul_rn(__fadd_rn(fmaxf(w[0], w[1]), fmaxf(w[1], w[2])), 0.5f), 0.01f), 1e-5f);
+                    }
+                    my[c] = v; part += v;
+                }
+                const float total = warp_sum(part);
+                float csum = 0.f;
+#pragma unroll
+                for (int c = 0; c < (S + 31) / 32; ++c) {
+                    const int k = c * 32 + lane;
+                    const float incl = warp_scan_add(k < nb ? __fdiv_rn(my[c], total) : 0.f, lane) + csum;
+                    if (k < nb) i_cdf[rl * S + k + 1] = incl;
+                    csum = __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) i_cdf[rl * S] = 0.f;
+            }
+            ebar();
+            for (int r = etid; r < kRowsG; r += 256) {   // thread per importance sample: inverse CDF
+                const int rl = r / S, f = r - rl * S;
+                const long long ray = ray0 + rl;
+                float val = INFINITY;
+                if (ray < a.R) {
+                    const float u = a.u_f ? a.u_f[ray * Sf + f] : philox_uniform(g.seed, (uint64_t)(ray * Sf + f), 1u);
+                    const float* cdf = i_cdf + rl * S;
+                    const float* t = st.t_c + rl * S;
+                    int lo = 0, hi = nb + 1;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+                    const int below = max(lo - 1, 0), above = min(lo, nb);
+                    const float c0 = cdf[below], c1 = cdf[above];
+                    const float b0 = __fmul_rn(0.5f, __fadd_rn(t[below], t[below + 1]));
+                    const float b1 = __fmul_rn(0.5f, __fadd_rn(t[above], t[above + 1]));
+                    float den = __fsub_rn(c1, c0);
+                    if (den < 1e-5f) den = 1.f;
+                    val = __fadd_rn(b0, __fmul_rn(__fdiv_rn(__fsub_rn(u, c0), den), __fsub_rn(b1, b0)));
+                }
+                i_tfu[r] = val;
+            }
+            ebar();
+            for (int r = etid; r < kRowsG; r += 256) {   // stable rank sort -> ascending importance depths
+                const int rl = r / S, j = r - rl * S;
+                const float tj = i_tfu[r];
+                const float4* row = reinterpret_cast<const float4*>(i_tfu + rl * S);
+                int rank = 0;
+#pragma unroll 4
+                for (int k4 = 0; k4 < S / 4; ++k4) {
+                    const float4 t4 = row[k4];
+                    const int k = 4 * k4;
+                    rank += (t4.x < tj || (t4.x == tj && k + 0 < j)) + (t4.y < tj || (t4.y == tj && k + 1 < j)) +
+                            (t4.z < tj || (t4.z == tj && k + 2 < j)) + (t4.w < tj || (t4.w == tj && k + 3 < j));
+                }
+                st.t_f[rl * Sf + rank] = tj;
+            }
+            ebar();
+            if (etid == 0) mbar_arrive(&sm.fine_ready[n & 3]);
+        };
+        // ---- merge + transmittance + omega for group n (renderer.py:289-301, ray_marcher.py:25-44), 256 threads
+        auto composite = [&](int n) {
+            GroupState& st = sm.st[n & 3];
+            SlotState& sl = sm.slot[n & 1];
+            const int grp = (int)blockIdx.x + n * (int)gridDim.x;
+            const long long ray0 = (long long)grp * GR;
+            float* m_t = sm.rscratch;                // [GR][L] = 768
+            float* m_sg = sm.rscratch + 768;
+            float* m_al = sm.rscratch + 1536;
+            float* m_fc = sm.rscratch + 2304;
+            ebar();
+            if (etid < GR * kRgb) sl.acc[etid >> 5][etid & 31] = 0.f;
+            for (int r = etid; r < 2 * kRowsG; r += 256) {
+                const bool is_f = r >= kRowsG;
+                const int row = is_f ? r - kRowsG : r;
+                const int rl = row / S, i = row - rl * S;
+                const float* tc = st.t_c + rl * S;
+                const float* tf = st.t_f + rl * Sf;
+                const bool rev = tc[0] > tc[S - 1];
+                if (!is_f) {
+                    const int ci = rev ? S - 1 - i : i;
+                    const float tv = tc[ci];
+                    int lo = 0, hi = Sf;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tf[mid] < tv) lo = mid + 1; else hi = mid; }
+                    const int pos = i + lo;
+                    m_t[rl * L + pos] = tv; m_sg[rl * L + pos] = st.sg_c[rl * S + ci]; sl.pos[rl * S + ci] = pos;
+                } else {
+                    const float tv = tf[i];
+                    int lo = 0, hi = S;
+                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tc[rev ? S - 1 - mid : mid] <= tv) lo = mid + 1; else hi = mid; }
+                    const int pos = i + lo;
+                    m_t[rl * L + pos] = tv; m_sg[rl * L + pos] = st.sg_f[row]; sl.pos[kRowsG + row] = pos;
+                }
+            }
+            ebar();
+            for (int r = etid; r < 2 * kRowsG; r += 256) {
+                const int i = r % L;
+                float alpha = 0.f, fac = 1.f;
+                if (i < L - 1) {
+                    const float smid = __fsub_rn(__fmul_rn(__fadd_rn(m_sg[r], m_sg[r + 1]), 0.5f), 1.f);
+                    alpha = 1.f - ex2_approx(-kLog2e * __fmul_rn(softplus_mufu(smid), m_t[r + 1] - m_t[r]));
+                    fac = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+                }
+                m_al[r] = alpha; m_fc[r] = fac;
+            }
+            ebar();
+            for (int rl = e; rl < GR; rl += kEW) {
+                const long long ray = ray0 + rl;
+                float carry = 1.f, acc_w = 0.f, acc_d = 0.f, wprev = 0.f;
+#pragma unroll
+                for (int c = 0; c < L / 32; ++c) {
+                    const int i = c * 32 + lane;
+                    const float incl = warp_scan_mul(m_fc[rl * L + i], lane);
+                    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                    if (lane == 0) excl = 1.f;
+                    const float wi = m_al[rl * L + i] * (carry * excl);
+                    carry *= __shfl_sync(0xffffffffu, incl, 31);
+                    acc_w += wi;
+                    if (i < L - 1) acc_d = fmaf(wi, __fmul_rn(__fadd_rn(m_t[rl * L + i], m_t[rl * L + i + 1]), 0.5f), acc_d);
+                    float wl = __shfl_up_sync(0xffffffffu, wi, 1);
+                    if (lane == 0) wl = wprev;
+                    wprev = __shfl_sync(0xffffffffu, wi, 31);
+                    sl.om[rl * L + i] = __fmul_rn(__fadd_rn(wl, wi), 0.5f);
+                }
+                const float wsum = warp_sum(acc_w), dnum = warp_sum(acc_d);
+                const float back = g.white_back ? __fsub_rn(1.f, wsum) : 0.f;
+                if (ray < a.R) {
+                    if (lane < 3) {
+                        const float v = fmaf(a.ro[ray * 3 + lane], wsum, a.rd[ray * 3 + lane] * dnum);
+                        a.out_xyz[ray * 3 + lane] = __fsub_rn(__fmul_rn(__fadd_rn(v, back), 2.f), 1.f);
+                    }
+                    if (lane == 0) {
+                        a.out_depth[ray] = __fdiv_rn(dnum, wsum);
+                        a.out_wsum[ray] = wsum;
+                        atomicMin(&a.bounds[0], float_to_ordered(m_t[rl * L]));
+                        atomicMax(&a.bounds[1], float_to_ordered(m_t[rl * L + L - 1]));
+                    }
+                }
+                if (lane == 0) sl.back[rl] = back;
+            }
+            ebar();
         };
         auto colours = [&](int n) {                                        // sum_j omega_j * rgb_j for group n, from TMEM
             const int slot_i = n & 1;
             SlotState& sl = sm.slot[slot_i];
-            mbar_wait(&sm.omega_ready[slot_i], (n >> 1) & 1);
             tc_fence_after();
             const int grp = (int)blockIdx.x + n * (int)gridDim.x;
             const long long ray0 = (long long)grp * GR;
@@ -435,13 +613,18 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             if (etid == 0) mbar_arrive(&sm.state_free[n & 3]);
         };
 
+        // after the sigma of a group's last coarse / fine tile has been read back: the per-ray phases of that group
+        auto after_sigma = [&](const TileDesc& tp) {
+            if (tp.k != 2) return;
+            if (tp.pass == 0) importance(tp.n);
+            else { composite(tp.n); colours(tp.n); }
+        };
         int it = 0;
         TileDesc prev{0, 0, 0};
         bool have_prev = false;
         for (int q = 0; q < T; ++q) {
             const TileDesc td = tile_at(q);
             if (td.n >= n_my) continue;
-            if (td.pass == 0 && td.k == 0 && td.n >= 2) colours(td.n - 2);   // frees the TMEM slot this group is about to reuse
             // ---- epilogue 1: D1 -> softplus2 -> A2[buf]
             mbar_wait(&sm.d1_full, it & 1);
             tc_fence_after();
@@ -472,184 +655,14 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.a2_full[buf]);
-            // ---- sigma of the PREVIOUS tile (its layer 2 has had a whole epilogue to finish)
-            if (have_prev) sigma_read(it - 1, prev);
+            // ---- sigma of the PREVIOUS tile (its layer 2 has had a whole epilogue to finish), then its group's per-ray phase
+            if (have_prev) { sigma_read(it - 1, prev); after_sigma(prev); }
             prev = td; have_prev = true;
             ++it;
             // odd tail: the next tile (F of the same, last group) waits on THIS tile's sigma -> do not defer it
-            if ((n_my & 1) && td.n == n_my - 1 && td.pass == 0 && td.k == 2) { sigma_read(it - 1, prev); have_prev = false; }
+            if ((n_my & 1) && td.n == n_my - 1 && td.pass == 0 && td.k == 2) { sigma_read(it - 1, prev); after_sigma(prev); have_prev = false; }
         }
-        if (have_prev) sigma_read(it - 1, prev);
-        for (int n = (n_my >= 2 ? n_my - 2 : 0); n < n_my; ++n) colours(n);
-    } else if (warp < kGW + kEW + kRW) {
-        // =========================================================================== RAYS
-        const int rw = warp - kGW - kEW;
-        float* scr = sm.rscratch[rw];
-        for (int u = 0; u * 2 < n_my; ++u) {
-            for (int phase = 0; phase < 4; ++phase) {                      // imp(A) imp(B) comp(A) comp(B)
-                const int n = 2 * u + (phase & 1);
-                if (n >= n_my) continue;
-                const int pass = phase >> 1;
-                GroupState& st = sm.st[n & 3];
-                SlotState& sl = sm.slot[n & 1];
-                const int grp = (int)blockIdx.x + n * (int)gridDim.x;
-                const long long ray0 = (long long)grp * GR;
-                mbar_wait(&sm.sigma_ready[n & 3][pass], (n >> 2) & 1);
-                if (pass == 0) {
-                    // ---------------- importance sampling, one ray at a time (renderer.py:328-387)
-                    for (int rl = rw; rl < GR; rl += kRW) {
-                        const long long ray = ray0 + rl;
-                        const float* t = st.t_c + rl * S;
-                        const float* sg = st.sg_c + rl * S;
-                        float* w = scr;                 // [S]
-                        float* cdf = scr + S;           // [S]
-                        float* tfu = scr + 2 * S;       // [S] unsorted
-                        constexpr int nb = S - 3;
-                        float carry = 1.f;
-#pragma unroll
-                        for (int c = 0; c < (S + 31) / 32; ++c) {
-                            const int i = c * 32 + lane;
-                            float alpha = 0.f, fac = 1.f;
-                            if (i < S - 1) {
-                                const float smid = __fsub_rn(__fmul_rn(__fadd_rn(sg[i], sg[i + 1]), 0.5f), 1.f);
-                                alpha = 1.f - ex2_approx(-kLog2e * __fmul_rn(softplus_mufu(smid), t[i + 1] - t[i]));
-                                fac = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
-                            }
-                            const float incl = warp_scan_mul(fac, lane);
-                            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-                            if (lane == 0) excl = 1.f;
-                            if (i < S - 1) w[i] = alpha * (carry * excl);
-                            carry *= __shfl_sync(0xffffffffu, incl, 31);
-                        }
-                        __syncwarp();
-                        float my[(S + 31) / 32];
-                        float part = 0.f;
-#pragma unroll
-                        for (int c = 0; c < (S + 31) / 32; ++c) {
-                            const int k = c * 32 + lane;
-                            float v = 0.f;
-                            if (k < nb) v = __fadd_rn(__fadd_rn(__fmul_rn(__fadd_rn(fmaxf(w[k], w[k + 1]), fmaxf(w[k + 1], w[k + 2])), 0.5f), 0.01f), 1e-5f);
-                            my[c] = v; part += v;
-                        }
-                        const float total = warp_sum(part);
-                        float csum = 0.f;
-#pragma unroll
-                        for (int c = 0; c < (S + 31) / 32; ++c) {
-                            const int k = c * 32 + lane;
-                            const float incl = warp_scan_add(k < nb ? __fdiv_rn(my[c], total) : 0.f, lane) + csum;
-                            if (k < nb) cdf[k + 1] = incl;
-                            csum = __shfl_sync(0xffffffffu, incl, 31);
-                        }
-                        if (lane == 0) cdf[0] = 0.f;
-                        __syncwarp();
-                        for (int f = lane; f < Sf; f += 32) {
-                            float val = INFINITY;
-                            if (ray < a.R) {
-                                const float u = a.u_f ? a.u_f[ray * Sf + f] : philox_uniform(g.seed, (uint64_t)(ray * Sf + f), 1u);
-                                int lo = 0, hi = nb + 1;
-                                while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
-                                const int below = max(lo - 1, 0), above = min(lo, nb);
-                                const float c0 = cdf[below], c1 = cdf[above];
-                                const float b0 = __fmul_rn(0.5f, __fadd_rn(t[below], t[below + 1]));
-                                const float b1 = __fmul_rn(0.5f, __fadd_rn(t[above], t[above + 1]));
-                                float den = __fsub_rn(c1, c0);
-                                if (den < 1e-5f) den = 1.f;
-                                val = __fadd_rn(b0, __fmul_rn(__fdiv_rn(__fsub_rn(u, c0), den), __fsub_rn(b1, b0)));
-                            }
-                            tfu[f] = val;
-                        }
-                        __syncwarp();
-                        for (int j = lane; j < Sf; j += 32) {              // stable rank sort
-                            const float tj = tfu[j];
-                            const float4* row = reinterpret_cast<const float4*>(tfu);
-                            int rank = 0;
-#pragma unroll 4
-                            for (int k4 = 0; k4 < S / 4; ++k4) {
-                                const float4 t4 = row[k4];
-                                const int k = 4 * k4;
-                                rank += (t4.x < tj || (t4.x == tj && k + 0 < j)) + (t4.y < tj || (t4.y == tj && k + 1 < j)) +
-                                        (t4.z < tj || (t4.z == tj && k + 2 < j)) + (t4.w < tj || (t4.w == tj && k + 3 < j));
-                            }
-                            st.t_f[rl * Sf + rank] = tj;
-                        }
-                        __syncwarp();
-                    }
-                    if (lane == 0) mbar_arrive(&sm.fine_ready[n & 3]);
-                } else {
-                    // ---------------- merge + transmittance + omega (renderer.py:289-301, ray_marcher.py:25-44)
-                    for (int rl = rw; rl < GR; rl += kRW) {
-                        const long long ray = ray0 + rl;
-                        const float* tc = st.t_c + rl * S;
-                        const float* tf = st.t_f + rl * Sf;
-                        float* m_t = scr;               // [L]
-                        float* m_sg = scr + L;          // [L]
-                        float* m_al = scr + 2 * L;      // [L]
-                        float* m_fc = scr + 3 * L;      // [L]
-                        const bool rev = tc[0] > tc[S - 1];
-                        for (int i = lane; i < S; i += 32) {
-                            const int ci = rev ? S - 1 - i : i;
-                            const float tv = tc[ci];
-                            int lo = 0, hi = Sf;
-                            while (lo < hi) { const int mid = (lo + hi) >> 1; if (tf[mid] < tv) lo = mid + 1; else hi = mid; }
-                            const int pos = i + lo;
-                            m_t[pos] = tv; m_sg[pos] = st.sg_c[rl * S + ci]; sl.pos[rl * S + ci] = pos;
-                        }
-                        for (int j = lane; j < Sf; j += 32) {
-                            const float tv = tf[j];
-                            int lo = 0, hi = S;
-                            while (lo < hi) { const int mid = (lo + hi) >> 1; if (tc[rev ? S - 1 - mid : mid] <= tv) lo = mid + 1; else hi = mid; }
-                            const int pos = j + lo;
-                            m_t[pos] = tv; m_sg[pos] = st.sg_f[rl * Sf + j]; sl.pos[kRowsG + rl * Sf + j] = pos;
-                        }
-                        __syncwarp();
-                        for (int i = lane; i < L; i += 32) {
-                            float alpha = 0.f, fac = 1.f;
-                            if (i < L - 1) {
-                                const float smid = __fsub_rn(__fmul_rn(__fadd_rn(m_sg[i], m_sg[i + 1]), 0.5f), 1.f);
-                                alpha = 1.f - ex2_approx(-kLog2e * __fmul_rn(softplus_mufu(smid), m_t[i + 1] - m_t[i]));
-                                fac = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
-                            }
-                            m_al[i] = alpha; m_fc[i] = fac;
-                        }
-                        __syncwarp();
-                        float carry = 1.f, acc_w = 0.f, acc_d = 0.f, wprev = 0.f;
-#pragma unroll
-                        for (int c = 0; c < L / 32; ++c) {
-                            const int i = c * 32 + lane;
-                            const float incl = warp_scan_mul(m_fc[i], lane);
-                            float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-                            if (lane == 0) excl = 1.f;
-                            const float wi = m_al[i] * (carry * excl);
-                            carry *= __shfl_sync(0xffffffffu, incl, 31);
-                            acc_w += wi;
-                            if (i < L - 1) acc_d = fmaf(wi, __fmul_rn(__fadd_rn(m_t[i], m_t[i + 1]), 0.5f), acc_d);
-                            float wl = __shfl_up_sync(0xffffffffu, wi, 1);
-                            if (lane == 0) wl = wprev;
-                            wprev = __shfl_sync(0xffffffffu, wi, 31);
-                            sl.om[rl * L + i] = __fmul_rn(__fadd_rn(wl, wi), 0.5f);
-                        }
-                        const float wsum = warp_sum(acc_w), dnum = warp_sum(acc_d);
-                        const float back = g.white_back ? __fsub_rn(1.f, wsum) : 0.f;
-                        sl.acc[rl][lane] = 0.f;
-                        if (ray < a.R) {
-                            if (lane < 3) {
-                                const float v = fmaf(a.ro[ray * 3 + lane], wsum, a.rd[ray * 3 + lane] * dnum);
-                                a.out_xyz[ray * 3 + lane] = __fsub_rn(__fmul_rn(__fadd_rn(v, back), 2.f), 1.f);
-                            }
-                            if (lane == 0) {
-                                a.out_depth[ray] = __fdiv_rn(dnum, wsum);
-                                a.out_wsum[ray] = wsum;
-                                atomicMin(&a.bounds[0], float_to_ordered(m_t[0]));
-                                atomicMax(&a.bounds[1], float_to_ordered(m_t[L - 1]));
-                            }
-                        }
-                        if (lane == 0) sl.back[rl] = back;
-                        __syncwarp();
-                    }
-                    if (lane == 0) mbar_arrive(&sm.omega_ready[n & 1]);
-                }
-            }
-        }
+        if (have_prev) { sigma_read(it - 1, prev); after_sigma(prev); }
     } else {
         // =========================================================================== MMA issuer (one thread)
         if (lane == 0) {
