@@ -14,6 +14,7 @@
 // tiles, F = importance tiles): every dependency - importance depths for F(A), TMEM/state reuse for C(A') - has
 // three tiles of independent gather work in front of it, so the loads never stop.  Colour logits of both groups
 // stay in TMEM (2 x 6 tiles x 32 columns) next to D1 (64) and the sigma accumulator (16): 464 of 512 columns.
+#include <stdlib.h>
 #include "render_device.cuh"
 
 namespace p3d {
@@ -72,6 +73,14 @@ struct WsArgs {
     int n_groups, single_pass;
     int srow, scol, splane;
     float sigma_cull;
+    unsigned long long* timing;      // optional [16] cycle counters (debug: P3D_WS_TIMING=1), nullptr = off
+};
+
+// cycle accounting of one gather warp and one epilogue warp of CTA 0 (debug aid, off by default)
+struct Tick {
+    unsigned long long* dst; long long t0; bool on;
+    __device__ Tick(unsigned long long* d, bool enable) : dst(d), t0(0), on(enable && d != nullptr) { if (on) t0 = clock64(); }
+    __device__ void lap(int slot) { if (on) { const long long t1 = clock64(); atomicAdd(dst + slot, (unsigned long long)(t1 - t0)); t0 = t1; } }
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -249,6 +258,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
     if (warp < kGW) {
         // =========================================================================== GATHER
         const int gw = warp, team = gw >> 2, wt = gw & 3;
+        Tick tk_(a.timing, blockIdx.x == 0 && gw == 0 && lane == 0);
         int it = 0;
         for (int q = 0; q < T; ++q) {
             const TileDesc td = tile_at(q);
@@ -258,10 +268,13 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             const int grp = (int)blockIdx.x + td.n * (int)gridDim.x;
             const long long ray0 = (long long)grp * GR;
             GroupState& st = sm.st[td.n & 3];
+            tk_.lap(0);
             if (td.pass == 0) mbar_wait(&sm.state_free[td.n & 3], ((td.n >> 2) & 1) ^ 1);
             else mbar_wait(&sm.fine_ready[td.n & 3], (td.n >> 2) & 1);
+            tk_.lap(1);                                                   // [1] wait state_free / fine_ready
             const int stage = my_it % kNA;
             mbar_wait(&sm.a1_empty[stage], ((my_it / kNA) & 1) ^ 1);
+            tk_.lap(2);                                                   // [2] wait a1_empty
             const int view = (int)(ray0 / g.M);
             const void* vplanes = BF16 ? (const void*)(reinterpret_cast<const __nv_bfloat16*>(a.planes) + (long long)view * g.stride_view)
                                        : (const void*)(reinterpret_cast<const float*>(a.planes) + (long long)view * g.stride_view);
@@ -361,6 +374,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.a1_full[stage]);
+            tk_.lap(3);                                                   // [3] taps + gather of one tile (32 rows)
         }
     } else if (warp < kGW + kEW) {
         // =========================================================================== EPILOGUE
@@ -619,6 +633,13 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             if (tp.pass == 0) importance(tp.n);
             else { composite(tp.n); colours(tp.n); }
         };
+        Tick tk_(a.timing, blockIdx.x == 0 && e == 0 && lane == 0);
+        // after the sigma read: per-ray phases, timed separately
+        auto after_sigma_t = [&](const TileDesc& tp) {
+            if (tp.k != 2) return;
+            if (tp.pass == 0) { importance(tp.n); tk_.lap(9); }           // [9] importance
+            else { composite(tp.n); tk_.lap(10); colours(tp.n); tk_.lap(11); }   // [10] merge/weights [11] colours
+        };
         int it = 0;
         TileDesc prev{0, 0, 0};
         bool have_prev = false;
@@ -626,7 +647,9 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             const TileDesc td = tile_at(q);
             if (td.n >= n_my) continue;
             // ---- epilogue 1: D1 -> softplus2 -> A2[buf]
+            tk_.lap(4);
             mbar_wait(&sm.d1_full, it & 1);
+            tk_.lap(5);                                                   // [5] wait d1_full
             tc_fence_after();
             float v[32];
             tmem_ld32(tmem + kColD1 + lane_base + 32 * chunk, v);
@@ -634,7 +657,9 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.d1_empty);
             const int buf = it & 1;
+            tk_.lap(6);                                                   // [6] tcgen05.ld D1
             mbar_wait(&sm.a2_empty[buf], ((it >> 1) & 1) ^ 1);
+            tk_.lap(7);                                                   // [7] wait a2_empty
             {
                 const int trow = quarter * 32 + lane;
                 unsigned char* a2h = sm.a2[buf][0];
@@ -655,14 +680,15 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.a2_full[buf]);
+            tk_.lap(8);                                                   // [8] softplus / split / A2 stores
             // ---- sigma of the PREVIOUS tile (its layer 2 has had a whole epilogue to finish), then its group's per-ray phase
-            if (have_prev) { sigma_read(it - 1, prev); after_sigma(prev); }
+            if (have_prev) { sigma_read(it - 1, prev); tk_.lap(12); after_sigma_t(prev); }   // [12] sigma read-back (incl. wait d2_full)
             prev = td; have_prev = true;
             ++it;
             // odd tail: the next tile (F of the same, last group) waits on THIS tile's sigma -> do not defer it
-            if ((n_my & 1) && td.n == n_my - 1 && td.pass == 0 && td.k == 2) { sigma_read(it - 1, prev); after_sigma(prev); have_prev = false; }
+            if ((n_my & 1) && td.n == n_my - 1 && td.pass == 0 && td.k == 2) { sigma_read(it - 1, prev); after_sigma_t(prev); have_prev = false; }
         }
-        if (have_prev) { sigma_read(it - 1, prev); after_sigma(prev); }
+        if (have_prev) { sigma_read(it - 1, prev); after_sigma_t(prev); }
     } else {
         // =========================================================================== MMA issuer (one thread)
         if (lane == 0) {
@@ -772,6 +798,13 @@ int render_forward_fused_ws(const Geom& g, const p3d_render_params* p, const voi
         P3D_CUDA_TRY(cudaGetDevice(&dev));
         P3D_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
+    static unsigned long long* d_timing = nullptr;
+    static const bool timing_on = getenv("P3D_WS_TIMING") != nullptr;
+    if (timing_on) {
+        if (!d_timing) P3D_CUDA_TRY(cudaMalloc(&d_timing, 16 * sizeof(unsigned long long)));
+        P3D_CUDA_TRY(cudaMemsetAsync(d_timing, 0, 16 * sizeof(unsigned long long), stream));
+        a.timing = d_timing;
+    }
     const size_t smem = sizeof(WsSmem) + 1024;
     void (*kern)(WsArgs) = nullptr;
     if (g.S == 96) kern = p->planes_bf16 ? k_render_ws<true, 96> : k_render_ws<false, 96>;
@@ -782,6 +815,17 @@ int render_forward_fused_ws(const Geom& g, const p3d_render_params* p, const voi
         ProfileScope prof(PROF_FUSED, stream);
         kern<<<grid, kThreadsWS, smem, stream>>>(a);
         P3D_LAUNCH_CHECK();
+    }
+    if (timing_on) {
+        unsigned long long h[16];
+        P3D_CUDA_TRY(cudaMemcpyAsync(h, d_timing, sizeof(h), cudaMemcpyDeviceToHost, stream));
+        P3D_CUDA_TRY(cudaStreamSynchronize(stream));
+        const int groups_cta0 = (a.n_groups + grid - 1) / grid;
+        fprintf(stderr, "[p3d ws timing, CTA0, cycles/group over %d groups] G(warp0: 1/3 of tiles): wait_dep %.0f wait_ring %.0f gather %.0f | "
+                        "E(warp0): wait_d1 %.0f ld_d1 %.0f wait_a2 %.0f epi1 %.0f sigma %.0f importance %.0f merge %.0f colours %.0f other %.0f\n",
+                groups_cta0, (double)h[1] / groups_cta0, (double)h[2] / groups_cta0, (double)h[3] / groups_cta0, (double)h[5] / groups_cta0,
+                (double)h[6] / groups_cta0, (double)h[7] / groups_cta0, (double)h[8] / groups_cta0, (double)h[12] / groups_cta0,
+                (double)h[9] / groups_cta0, (double)h[10] / groups_cta0, (double)h[11] / groups_cta0, (double)(h[0] + h[4]) / groups_cta0);
     }
     if (p->defer_depth_clamp) return P3D_OK;
     return launch_depth_finalize(out_depth, R, ws.bounds, stream);

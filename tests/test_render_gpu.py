@@ -315,3 +315,24 @@ def test_renderer_no_grad_path_unchanged_and_grad_path_equal():
     assert all(t.requires_grad for t in b)
     for x, y in zip(a, b):
         assert torch.equal(x, y.detach())
+
+
+def test_fused_v2_kernel_still_matches(tmp_path):
+    """The 2-CTA/SM bulk-synchronous fused kernel (P3D_FUSED_IMPL=v2) is kept selectable; the env switch is read once
+    per process, so run it in a child process."""
+    import os, subprocess, sys, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent('''
+        import sys; sys.path.insert(0, %r)
+        from tests.test_render_gpu import gpu_render, TOL
+        from tests.helpers import load_golden
+        for name in ("config1", "mid_eval96"):
+            g = load_golden("render", name)
+            out, _ = gpu_render(g["case"], mlp_mode=1)
+            for got, key in zip(out, ("rgb", "depth", "wsum", "xyz")):
+                err = (got - g[key]).abs()
+                assert (err < TOL).float().mean().item() > 0.999 and err.max().item() < 2e-2, (name, key, err.max().item())
+        print("ok")
+    ''' % root)
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=dict(os.environ, P3D_FUSED_IMPL='v2'))
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
