@@ -37,7 +37,7 @@ def workload_config(n_gpus, mlp_mode='tc_3xbf16', planes='fp32'):
     return {'workload': f'{VIEWS} views/GPU x {R}x{R} rays x ({S}+{SF}) samples, {VIEWS} distinct 3x{C}x{P}x{P} fp32 tri-planes/GPU',
             'views_per_gpu': VIEWS, 'rays': R * R, 'samples_coarse': S, 'samples_importance': SF, 'plane': P,
             'decoder': '32-64-33 softplus', 'mlp_mode': mlp_mode, 'plane_storage': planes, 'parallelism': f'views sharded x{n_gpus}',
-            'l2': 'inputs (805 MB planes + 3.4 GB scratch per step) exceed the 126 MB L2; no explicit flush'}
+            'l2': 'inputs (805 MB of tri-planes re-laid out every step) exceed the 126 MB L2; no explicit flush'}
 
 
 def read_peaks():
@@ -270,8 +270,12 @@ def run_ours(args):
             roof = {'bound': 'tensor', 'achieved': flops / (kern_ms * 1e-3) / 1e12, 'peak': tc_tf, 'unit': 'TFLOP/s'}
         else:
             roof = {'bound': 'hbm', 'achieved': byts / (kern_ms * 1e-3) / 1e9, 'peak': hbm_gbs, 'unit': 'GB/s'}
-        roof.update({'frac': roof['achieved'] / roof['peak'], 'traffic': None,
-                     'kernel': 'k_render_fused' if fused else 'k_sample_decode', 'kernel_ms_per_launch': kern_ms,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
+        # command (profiles/r1_v3b_fused_raw.csv: 630.5 MB + 21.9 MB); only valid for the default kernel / workload
+        traffic = 652.4e6 if (fused and args.planes == 'fp32' and os.environ.get('P3D_FUSED_IMPL', '') != 'v2') else None
+        roof.update({'frac': roof['achieved'] / roof['peak'], 'traffic': traffic,
+                     'kernel': ('k_render_ws' if os.environ.get('P3D_FUSED_IMPL', '') != 'v2' else 'k_render_fused') if fused else 'k_sample_decode',
+                     'kernel_ms_per_launch': kern_ms,
                      'launches_timed': int(slot_n[slot]), 'peak_source': peak_src,
                      'step_breakdown_ms': {'sample_decode': slot_ms[0] / 3, 'importance': slot_ms[1] / 3, 'composite': slot_ms[2] / 3,
                                            'layout': slot_ms[3] / 3, 'raygen': slot_ms[4] / 3, 'fused': slot_ms[5] / 3}})
