@@ -93,10 +93,12 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    for (int it = 0; it < (1 << 24); ++it) {             // try_wait suspends in hardware; the cap turns a protocol bug into a trap
+    for (int it = 0; it < (1 << 17); ++it) {             // ~20 us per try: the cap turns a protocol bug into a trap after ~2 s
         uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        // the suspend-time hint lets a waiting warp sleep in hardware instead of polling: roles that run ahead of the
+        // critical path must not steal issue slots from it
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
         if (ok) return;
     }
     asm volatile("trap;");

@@ -336,3 +336,90 @@ def test_fused_v2_kernel_still_matches(tmp_path):
     ''' % root)
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=dict(os.environ, P3D_FUSED_IMPL='v2'))
     assert r.returncode == 0 and 'ok' in r.stdout, r.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases: empty and ragged inputs, unusual sample counts, error behaviour
+# ---------------------------------------------------------------------------------------------
+def _tiny(dev, N=1, M=5, P=8, seed=0):
+    from panic3d_b200.training.triplane import OSGDecoder
+    g = torch.Generator().manual_seed(seed)
+    planes = torch.randn(N, 3, 32, P, P, generator=g)
+    dec = OSGDecoder(32, {'decoder_lr_mul': 1, 'decoder_output_dim': 32}).requires_grad_(False)
+    ro = torch.tensor([0.0, 0.0, 1.0]).expand(N, M, 3).contiguous()
+    rd = torch.nn.functional.normalize(torch.randn(N, M, 3, generator=g) * 0.1 + torch.tensor([0.0, 0.0, -1.0]), dim=-1)
+    return planes, dec, ro, rd
+
+
+def test_empty_batch_and_single_ray():
+    from panic3d_b200.training.volumetric_rendering.renderer import ImportanceRenderer
+    dev = _dev()
+    r = ImportanceRenderer(use_triplane=True)
+    opts = dict(orc.DEFAULT_OPTS, depth_resolution=8, depth_resolution_importance=8)
+    planes, dec, ro, rd = _tiny(dev, N=1, M=1)
+    with torch.no_grad():
+        out = r(planes.to(dev), dec.to(dev), ro.to(dev), rd.to(dev), opts)
+        assert [tuple(o.shape) for o in out] == [(1, 1, 32), (1, 1, 1), (1, 1, 1), (1, 1, 3)]
+        assert all(torch.isfinite(o).all() for o in out)
+        # zero views: empty outputs, no launch, no error
+        out0 = r(planes[:0].to(dev), dec.to(dev), ro[:0].to(dev), rd[:0].to(dev), opts)
+        assert [tuple(o.shape) for o in out0] == [(0, 1, 32), (0, 1, 1), (0, 1, 1), (0, 1, 3)]
+        pts = r.run_model(planes.to(dev), dec.to(dev), torch.zeros(1, 0, 3, device=dev), None, opts)
+        assert tuple(pts['rgb'].shape) == (1, 0, 32) and tuple(pts['sigma'].shape) == (1, 0, 1)
+
+
+@pytest.mark.parametrize('S,Sf,M', [(4, 3, 7), (5, 0, 33), (31, 17, 130), (64, 64, 3), (200, 56, 2)])
+def test_ragged_sample_counts_match_oracle(S, Sf, M):
+    """Ray counts that are not multiples of any tile size and odd sample counts (v1 path) against the oracle."""
+    from panic3d_b200.training.volumetric_rendering.renderer import ImportanceRenderer
+    dev = _dev()
+    planes, dec_m, ro, rd = _tiny(dev, N=2, M=M, P=16, seed=S * 100 + Sf)
+    opts = dict(orc.DEFAULT_OPTS, depth_resolution=S, depth_resolution_importance=Sf)
+    g = torch.Generator().manual_seed(1)
+    u_c, u_f = torch.rand(2, M, S, 1, generator=g), torch.rand(2 * M, max(Sf, 1), generator=g)[:, :Sf]
+    r = ImportanceRenderer(use_triplane=True)
+    r.injected_noise = (u_c, u_f)
+    with torch.no_grad():
+        out = r(planes.to(dev), dec_m.to(dev), ro.to(dev), rd.to(dev), opts)
+    dec = dict(w1=dec_m.net[0].weight.detach(), b1=dec_m.net[0].bias.detach(), w2=dec_m.net[2].weight.detach(), b2=dec_m.net[2].bias.detach())
+    ref = orc.render(planes, dec, ro, rd, opts, u_c, u_f if Sf > 0 else None, use_triplane=True)
+    for o, o_ref in zip(out, ref):
+        assert (o.cpu() - o_ref).abs().max().item() < TIGHT
+
+
+def test_fused_handles_ray_counts_that_leave_partial_groups():
+    """M = 12 rays (3 fused groups of 4 at S=96) and N = 3 views: odd number of groups per CTA, tail tiles."""
+    from panic3d_b200.training.volumetric_rendering.renderer import ImportanceRenderer
+    dev = _dev()
+    planes, dec_m, ro, rd = _tiny(dev, N=3, M=12, P=16, seed=5)
+    opts = dict(orc.DEFAULT_OPTS)
+    g = torch.Generator().manual_seed(2)
+    u_c, u_f = torch.rand(3, 12, 96, 1, generator=g), torch.rand(36, 96, generator=g)
+    outs = []
+    for mode in (0, 1):
+        r = ImportanceRenderer(use_triplane=True)
+        r.mlp_mode = mode
+        r.injected_noise = (u_c, u_f)
+        with torch.no_grad():
+            outs.append(r(planes.to(dev), dec_m.to(dev), ro.to(dev), rd.to(dev), opts))
+    for a_, b_ in zip(*outs):
+        assert (a_ - b_).abs().max().item() < 1e-4
+
+
+def test_bad_inputs_raise():
+    from panic3d_b200.training.volumetric_rendering.renderer import ImportanceRenderer
+    dev = _dev()
+    planes, dec, ro, rd = _tiny(dev)
+    r = ImportanceRenderer(use_triplane=True)
+    opts = dict(orc.DEFAULT_OPTS, depth_resolution=8, depth_resolution_importance=8)
+    with torch.no_grad():
+        with pytest.raises(NotImplementedError):
+            r(planes.to(dev), dec.to(dev), ro.to(dev), rd.to(dev), dict(opts, triplane_depth=2))
+        with pytest.raises(NotImplementedError):
+            r(planes.to(dev), dec.to(dev), ro.to(dev), rd.to(dev), dict(opts, density_noise=0.1))
+        with pytest.raises(RuntimeError):
+            r(planes.to(dev), dec.to(dev), ro.to(dev), rd.to(dev), dict(opts, depth_resolution=1))          # < 2 coarse samples
+        with pytest.raises(RuntimeError, match='unsupported'):
+            r(planes[:, :, :16].to(dev), dec.to(dev), ro.to(dev), rd.to(dev), opts)                       # 16-channel planes
+        with pytest.raises(ValueError):
+            r(planes[:, :2].to(dev), dec.to(dev), ro.to(dev), rd.to(dev), opts)                           # two planes
