@@ -37,7 +37,8 @@ def timeit(fn, flush_buf, iters=20, warm=5):
         if flush_buf is not None:
             flush_buf.add_(1)                      # evict: write a buffer larger than L2
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        torch.cuda._sleep(2_000_000)               # ~1 ms of GPU idle-spin: the host enqueues fn() behind it, so the
+        e0.record()                                # bracket sees device time only, not Python/ctypes launch latency
         fn()
         e1.record()
         torch.cuda.synchronize()

@@ -230,9 +230,9 @@ uint64_t p3d_launch_count(void) { return g_launches.load(); }
 
 int p3d_planes_to_channels_last(const float* planes_nchw, void* planes_cl, int64_t n_planes, int32_t channels,
                                 int32_t h, int32_t w, int32_t out_bf16, void* stream) {
-    P3D_REQUIRE(planes_nchw && planes_cl, "null plane pointer");
     P3D_REQUIRE(n_planes >= 0 && n_planes < 65536 && channels > 0 && h > 0 && w > 0, "bad plane sizes");
-    if (n_planes == 0) return P3D_OK;
+    if (n_planes == 0) return P3D_OK;                       // empty batch: nothing to do, pointers may be NULL
+    P3D_REQUIRE(planes_nchw && planes_cl, "null plane pointer");
     const long long HW = (long long)h * w;
     dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((channels + 31) / 32), (unsigned)n_planes), block(32, 8);
     ProfileScope prof(PROF_LAYOUT, (cudaStream_t)stream);
@@ -302,11 +302,11 @@ int p3d_render_forward(const p3d_render_params* p, const void* planes, const flo
     Geom g;
     int rc = make_geom(p, &g);
     if (rc) return rc;
-    P3D_REQUIRE(planes && w1 && b1 && w2 && b2 && ray_origins && ray_dirs, "null input pointer");
-    P3D_REQUIRE(out_rgb && out_depth && out_wsum && out_xyz, "null output pointer");
     P3D_REQUIRE(p->ray_mode == P3D_RAYS_NUMERIC || p->ray_mode == P3D_RAYS_AUTOBOX, "bad ray_mode %d", p->ray_mode);
     P3D_REQUIRE(!(p->ray_mode == P3D_RAYS_AUTOBOX && p->disparity), "disparity sampling needs numeric ray limits");
-    if ((long long)g.N * g.M == 0) return P3D_OK;
+    if ((long long)g.N * g.M == 0) return P3D_OK;           // empty batch: empty outputs, pointers may be NULL
+    P3D_REQUIRE(planes && w1 && b1 && w2 && b2 && ray_origins && ray_dirs, "null input pointer");
+    P3D_REQUIRE(out_rgb && out_depth && out_wsum && out_xyz, "null output pointer");
     Workspace ws;
     const size_t need = workspace_layout(p, workspace, &ws);
     if (!workspace || workspace_bytes < need) {
@@ -370,8 +370,9 @@ int p3d_decode_points(const p3d_render_params* p, const void* planes, const floa
     Geom g;
     int rc = make_geom(p, &g);
     if (rc) return rc;
-    P3D_REQUIRE(planes && w1 && b1 && w2 && b2 && coords && out_rgb && out_sigma, "null pointer");
     P3D_REQUIRE(n_points_per_view >= 0, "negative point count");
+    if ((long long)g.N * n_points_per_view == 0) return P3D_OK;
+    P3D_REQUIRE(planes && w1 && b1 && w2 && b2 && coords && out_rgb && out_sigma, "null pointer");
     return decode_points_v1(g, p, planes, w1, b1, w2, b2, coords, n_points_per_view, out_rgb, out_sigma, (cudaStream_t)stream);
 }
 

@@ -89,40 +89,90 @@ __device__ __forceinline__ S bias_act_elem(int G, S x, S b, S xref, S yref, S dy
 
 template <typename T, int VEC> struct alignas(sizeof(T) * VEC) Vec { T v[VEC]; };
 
-template <typename T, int A, int VEC>
+// BIAS: 0 = no bias, 1 = one bias per vector (NCHW-like: step_b % VEC == 0), 2 = contiguous bias run per vector
+// (channels-last / (N,C): step_b == 1, size_b % VEC == 0, bias 16-byte aligned), 3 = generic per-element index,
+// 4 = row mode (NCHW with >= 128 vectors per (n,c) image: the bias is CTA-uniform).
+// numel <= 2^31-1 is enforced at the ABI, so all index arithmetic is 32-bit unsigned (a 64-bit div/mod per vector was
+// the dominant cost of the first version on channels-last inputs).
+template <typename T, int A, int VEC, int BIAS, bool FWD>
 __global__ void __launch_bounds__(256) k_bias_act(const BiasActParams p) {
     using S = typename Elem<T>::acc;
     using V = Vec<T, VEC>;
+    constexpr bool REFS = !FWD;                                   // FWD: plain forward (G = 0, no xref/yref/dy) - the hot case
+    const int G = FWD ? 0 : p.grad;
+    constexpr int UNROLL = FWD ? 4 : 2;                            // independent 16-byte vectors in flight per thread
+    constexpr unsigned kItem = 256 * UNROLL;                       // vectors per CTA iteration (contiguous)
     const S alpha = (S)p.alpha, gain = (S)p.gain, clamp = (S)p.clamp;
     const T* bp = reinterpret_cast<const T*>(p.b);
-    const long long nvec = p.numel / VEC;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const bool shared_bias = bp && (p.step_b % VEC == 0);          // NCHW-like: one bias per vector
-    for (long long vi = (long long)blockIdx.x * blockDim.x + threadIdx.x; vi < nvec; vi += stride) {
-        const long long e0 = vi * VEC;
-        V xv = reinterpret_cast<const V*>(p.x)[vi];
-        V xr, yr, dv;
-        if (p.xref) xr = reinterpret_cast<const V*>(p.xref)[vi];
-        if (p.yref) yr = reinterpret_cast<const V*>(p.yref)[vi];
-        if (p.dy) dv = reinterpret_cast<const V*>(p.dy)[vi];
-        S bshared = (S)0;
-        long long bi0 = 0;
-        const long long ge = e0 + p.base;
-        if (bp) {
-            bi0 = (ge / p.step_b) % p.size_b;
-            if (shared_bias) bshared = Elem<T>::ld(bp[bi0]);
-        }
-        V out;
+    const unsigned nvec = (unsigned)(p.numel / VEC);
+    const unsigned step_b = (unsigned)p.step_b, size_b = (unsigned)p.size_b, base = (unsigned)p.base;
+    // BIAS == 4 walks the tensor row by row (a row = step_b elements sharing one bias), so the bias index is one
+    // uniform div/mod per CTA iteration; the other modes see a single row of nvec vectors.
+    const unsigned row_vecs = (BIAS == 4) ? step_b / VEC : nvec;
+    const unsigned items_per_row = (row_vecs + kItem - 1) / kItem;
+    const unsigned n_items = (nvec / row_vecs) * items_per_row;
+    for (unsigned item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const unsigned r = item / items_per_row, kk = (item - r * items_per_row) * kItem + threadIdx.x;
+        const unsigned vrow = r * row_vecs;
+        V xv[UNROLL], xr[UNROLL], yr[UNROLL], dv[UNROLL];
+        bool live[UNROLL];
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-            S b = bshared;
-            if (bp && !shared_bias) b = Elem<T>::ld(bp[p.step_b == 1 ? (bi0 + k) % p.size_b : ((ge + k) / p.step_b) % p.size_b]);
-            out.v[k] = Elem<T>::st(bias_act_elem<S, A>(p.grad, Elem<T>::ld(xv.v[k]), b, p.xref ? Elem<T>::ld(xr.v[k]) : (S)0,
-                                                       p.yref ? Elem<T>::ld(yr.v[k]) : (S)0, p.dy ? Elem<T>::ld(dv.v[k]) : (S)1,
-                                                       alpha, gain, clamp));
+        for (int u = 0; u < UNROLL; ++u) {
+            const unsigned vi = vrow + kk + u * 256;
+            live[u] = kk + u * 256 < row_vecs;
+            if (live[u]) {
+                xv[u] = reinterpret_cast<const V*>(p.x)[vi];
+                if (REFS) {
+                    if (p.xref) xr[u] = reinterpret_cast<const V*>(p.xref)[vi];
+                    if (p.yref) yr[u] = reinterpret_cast<const V*>(p.yref)[vi];
+                    if (p.dy) dv[u] = reinterpret_cast<const V*>(p.dy)[vi];
+                }
+            }
         }
-        reinterpret_cast<V*>(p.y)[vi] = out;
+        S brow = (S)0;
+        if (BIAS == 4) brow = Elem<T>::ld(bp[r % size_b]);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            if (!live[u]) continue;
+            const unsigned vi = vrow + kk + u * 256;
+            const unsigned ge = vi * VEC + base;
+            S bshared = brow;
+            V bv;
+            unsigned bi0 = 0;
+            if (BIAS == 1) bshared = Elem<T>::ld(bp[(ge / step_b) % size_b]);
+            if (BIAS == 2) bv = *reinterpret_cast<const V*>(bp + ge % size_b);
+            if (BIAS == 3) bi0 = (step_b == 1) ? ge % size_b : 0;
+            V out;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                S b = bshared;
+                if (BIAS == 2) b = Elem<T>::ld(bv.v[k]);
+                if (BIAS == 3) b = Elem<T>::ld(bp[step_b == 1 ? (bi0 + k) % size_b : ((ge + k) / step_b) % size_b]);
+                out.v[k] = Elem<T>::st(bias_act_elem<S, A>(G, Elem<T>::ld(xv[u].v[k]), b,
+                                                           (REFS && p.xref) ? Elem<T>::ld(xr[u].v[k]) : (S)0,
+                                                           (REFS && p.yref) ? Elem<T>::ld(yr[u].v[k]) : (S)0,
+                                                           (REFS && p.dy) ? Elem<T>::ld(dv[u].v[k]) : (S)1, alpha, gain, clamp));
+            }
+            reinterpret_cast<V*>(p.y)[vi] = out;
+        }
     }
+}
+
+template <typename T, int A, int VEC, int BIAS>
+void launch_bias_act_g(const BiasActParams& q, int grid, cudaStream_t stream) {
+    if (q.grad == 0 && !q.xref && !q.yref && !q.dy) k_bias_act<T, A, VEC, BIAS, true><<<grid, 256, 0, stream>>>(q);
+    else k_bias_act<T, A, VEC, BIAS, false><<<grid, 256, 0, stream>>>(q);
+}
+
+template <typename T, int A, int VEC>
+void launch_bias_act_v(const BiasActParams& q, int grid, cudaStream_t stream) {
+    auto aligned = [](const void* ptr) { return (reinterpret_cast<uintptr_t>(ptr) & 15) == 0; };
+    if (!q.b) launch_bias_act_g<T, A, VEC, 0>(q, grid, stream);
+    else if (q.step_b % VEC == 0 && q.step_b / VEC >= 128 && q.base == 0 && (q.numel / VEC) % (q.step_b / VEC) == 0)
+        launch_bias_act_g<T, A, VEC, 4>(q, grid, stream);
+    else if (q.step_b % VEC == 0) launch_bias_act_g<T, A, VEC, 1>(q, grid, stream);
+    else if (VEC > 1 && q.step_b == 1 && q.size_b % VEC == 0 && q.base % VEC == 0 && aligned(q.b)) launch_bias_act_g<T, A, VEC, 2>(q, grid, stream);
+    else launch_bias_act_g<T, A, VEC, 3>(q, grid, stream);
 }
 
 template <typename T, int A>
@@ -142,7 +192,7 @@ int launch_bias_act_t(const BiasActParams& p, cudaStream_t stream) {
         q.numel = main_n;
         const long long nvec = main_n / VEC;
         const int grid = (int)((nvec + 255) / 256 < (long long)n_sm * 8 ? (nvec + 255) / 256 : (long long)n_sm * 8);
-        k_bias_act<T, A, VEC><<<grid, 256, 0, stream>>>(q);
+        launch_bias_act_v<T, A, VEC>(q, grid, stream);
         P3D_LAUNCH_CHECK();
     }
     if (main_n < p.numel) {                                       // scalar tail (numel % VEC) or unaligned caller
@@ -156,7 +206,7 @@ int launch_bias_act_t(const BiasActParams& p, cudaStream_t stream) {
         q.base = main_n;
         const long long n = q.numel;
         const int grid = (int)((n + 255) / 256 < (long long)n_sm * 8 ? (n + 255) / 256 : (long long)n_sm * 8);
-        k_bias_act<T, A, 1><<<grid, 256, 0, stream>>>(q);
+        launch_bias_act_v<T, A, 1>(q, grid, stream);
         P3D_LAUNCH_CHECK();
     }
     return P3D_OK;

@@ -99,6 +99,204 @@ __global__ void __launch_bounds__(kThreads) k_upfirdn2d_tiled(const UpfirdnParam
     }
 }
 
+// ------------------------------------------------------------------------------------------ fast path (4x4 FIR)
+// The shapes panic3d's generator/discriminator hit: a 4x4 [1,3,3,1]^2 filter at (up,down) = (1,1) blur
+// after a transposed conv, (2,1) skip-image upsample, (1,2) discriminator downsample; W-contiguous in and out.
+// Persistent CTAs walk output tiles (128 x 32|16) with a two-stage cp.async pipeline:
+//   * the input footprint of tile i+1 streams into shared memory as ALIGNED 16-byte vectors while tile i is being
+//     computed.  Rows of odd-width images (513 x fp16 = 1026 B) are not 16-byte aligned, so each shared row is
+//     shifted by the row's own misalignment a_r = (address / sizeof(T)) mod VEC: the aligned global vector k of a row
+//     lands on the aligned shared vector k, and element q of the footprint sits at column a_r + q.  Vectors that
+//     straddle the image border (<= 2 per row) are assembled element-wise; rows above/below the image are zeros;
+//   * a thread owns 2 adjacent output columns x RPT consecutive rows.  Every input sample of its window is read from
+//     shared memory ONCE (conflict-free: a warp reads consecutive elements of one row) and scattered into the
+//     accumulators of the outputs it feeds - tap indices ky = sr*UP - r*DOWN, kx = sc*UP - e*DOWN are compile-time,
+//     so the polyphase structure (up=2 visits 2x2 of the 4x4 taps per output) costs nothing and the 16 taps live
+//     in registers;
+//   * fp32 accumulation for every storage type, one rounding at the store (as the reference's scalar_t=float path).
+template <typename T, int UP, int DOWN, int F>
+struct FastCfg {
+    static constexpr int VEC = 16 / (int)sizeof(T);
+    static constexpr int TW = 128;
+    static constexpr int RPT = (DOWN == 1) ? 8 : 4;
+    static constexpr int TH = 4 * RPT;
+    static constexpr int IN_W = ((TW - 1) * DOWN + F - 1) / UP + 1;
+    static constexpr int IN_H = ((TH - 1) * DOWN + F - 1) / UP + 1;
+    static constexpr int NIN = (DOWN + F - 1) / UP + 1;
+    static constexpr int NINROWS = ((RPT - 1) * DOWN + F - 1) / UP + 1;
+    static constexpr int PITCH = (IN_W + VEC - 1 + VEC - 1) / VEC * VEC;
+    static constexpr int NV = PITCH / VEC;
+    static constexpr size_t kBufBytes = (size_t)IN_H * PITCH * sizeof(T);
+    static constexpr size_t kSmem = 2 * kBufBytes + 2 * IN_H * sizeof(int);
+};
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <typename T, int UP, int DOWN, int F>
+__global__ void __launch_bounds__(kThreads) k_upfirdn2d_fast(const UpfirdnParams p, long long total_tiles, int pair_store) {
+    using Cfg = FastCfg<T, UP, DOWN, F>;
+    using V = uint4;
+    constexpr int VEC = Cfg::VEC, PITCH = Cfg::PITCH, NV = Cfg::NV, IN_H = Cfg::IN_H, RPT = Cfg::RPT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_buf[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw + Cfg::kBufBytes)};
+    int* s_a = reinterpret_cast<int*>(smem_raw + 2 * Cfg::kBufBytes);           // [2][IN_H] row shifts
+    const int tid = threadIdx.x;
+    const T* xp = reinterpret_cast<const T*>(p.x);
+    T* yp = reinterpret_cast<T*>(p.y);
+
+    float w[F * F];
+#pragma unroll
+    for (int i = 0; i < F * F; ++i) {
+        const int ky = i / F, kx = i % F;
+        const int sy = p.flip ? ky : F - 1 - ky, sx = p.flip ? kx : F - 1 - kx;
+        w[i] = p.f[sy * p.fsh + sx * p.fsw] * p.gain;
+    }
+    const long long tiles_per_img = (long long)p.tilesX * p.tilesY;
+
+    auto issue = [&](long long t, int b) {
+        const long long img = t / tiles_per_img;
+        const int rem = (int)(t - img * tiles_per_img);
+        const int tyi = rem / p.tilesX, txi = rem - tyi * p.tilesX;
+        const int n = (int)(img / p.C), c = (int)(img - (long long)n * p.C);
+        const int ix0 = (txi * Cfg::TW * DOWN - p.padx0) / UP, iy0 = (tyi * Cfg::TH * DOWN - p.pady0) / UP;   // exact
+        const T* xi = xp + n * p.xs[0] + c * p.xs[1];
+        T* sb = s_buf[b];
+        for (int i = tid; i < IN_H * NV; i += kThreads) {
+            const int r = i / NV, k = i - r * NV;
+            const int iy = iy0 + r;
+            V* dst = reinterpret_cast<V*>(sb + r * PITCH + k * VEC);
+            if (iy < 0 || iy >= p.inH) {
+                *dst = make_uint4(0u, 0u, 0u, 0u);
+                if (k == 0) s_a[b * IN_H + r] = 0;
+                continue;
+            }
+            const T* row0 = xi + (long long)iy * p.xs[2] + ix0;              // footprint element q = 0 (may be outside the row)
+            const int a = (int)((reinterpret_cast<uintptr_t>(row0) / sizeof(T)) & (VEC - 1));
+            if (k == 0) s_a[b * IN_H + r] = a;
+            const int ix = ix0 + k * VEC - a;                                // image column of the vector's first element
+            const T* src = row0 + (k * VEC - a);                             // 16-byte aligned
+            if (ix >= 0 && ix + VEC <= p.inW) {
+                cp_async16(dst, src);
+            } else {
+                alignas(16) T tmp[VEC];
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) tmp[j] = (ix + j >= 0 && ix + j < p.inW) ? src[j] : Px<T>::st(0.f);
+                *dst = *reinterpret_cast<const V*>(tmp);
+            }
+        }
+    };
+
+    long long t = blockIdx.x;
+    if (t >= total_tiles) return;
+    issue(t, 0);
+    cp_async_commit();
+    const int tx = tid & 63, tr = tid >> 6;
+    const int x0 = 2 * tx, y0 = tr * RPT;
+    const int bx = (x0 * DOWN) / UP, by = (y0 * DOWN) / UP;
+    int b = 0;
+    for (; t < total_tiles; t += gridDim.x, b ^= 1) {
+        const long long tn = t + gridDim.x;
+        if (tn < total_tiles) issue(tn, b ^ 1);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+
+        float acc[RPT][2];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) acc[r][0] = acc[r][1] = 0.f;
+        const T* sb = s_buf[b];
+#pragma unroll
+        for (int sr = 0; sr < Cfg::NINROWS; ++sr) {
+            const T* rowp = sb + (by + sr) * PITCH + s_a[b * IN_H + by + sr] + bx;
+            float v[Cfg::NIN];
+#pragma unroll
+            for (int sc = 0; sc < Cfg::NIN; ++sc) v[sc] = Px<T>::ld(rowp[sc]);
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const int ky = sr * UP - r * DOWN;
+                if (ky < 0 || ky >= F) continue;
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+#pragma unroll
+                    for (int sc = 0; sc < Cfg::NIN; ++sc) {
+                        const int kx = sc * UP - e * DOWN;
+                        if (kx < 0 || kx >= F) continue;
+                        acc[r][e] = fmaf(v[sc], w[ky * F + kx], acc[r][e]);
+                    }
+                }
+            }
+        }
+        {
+            const long long img = t / tiles_per_img;
+            const int rem = (int)(t - img * tiles_per_img);
+            const int tyi = rem / p.tilesX, txi = rem - tyi * p.tilesX;
+            const int n = (int)(img / p.C), c = (int)(img - (long long)n * p.C);
+            const int ox = txi * Cfg::TW + x0, oy0 = tyi * Cfg::TH + y0;
+            T* yi = yp + n * p.ys[0] + c * p.ys[1] + ox;
+            if (ox < p.outW) {
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const int oy = oy0 + r;
+                    if (oy >= p.outH) break;
+                    T* dst = yi + (long long)oy * p.ys[2];
+                    if (ox + 1 < p.outW) {
+                        if (pair_store) {
+                            struct alignas(2 * sizeof(T)) Pair { T a, b; };
+                            *reinterpret_cast<Pair*>(dst) = Pair{Px<T>::st(acc[r][0]), Px<T>::st(acc[r][1])};
+                        } else {
+                            dst[0] = Px<T>::st(acc[r][0]);
+                            dst[1] = Px<T>::st(acc[r][1]);
+                        }
+                    } else {
+                        dst[0] = Px<T>::st(acc[r][0]);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                                     // buffer b is free for the prefetch after next
+    }
+    cp_async_wait<0>();
+}
+
+template <typename T, int UP, int DOWN, int F>
+int launch_fast(UpfirdnParams p, int n_sm, cudaStream_t stream) {
+    using Cfg = FastCfg<T, UP, DOWN, F>;
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        P3D_CUDA_TRY(cudaFuncSetAttribute(k_upfirdn2d_fast<T, UP, DOWN, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+        P3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_upfirdn2d_fast<T, UP, DOWN, F>, kThreads, Cfg::kSmem));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    p.tilesX = (p.outW + Cfg::TW - 1) / Cfg::TW;
+    p.tilesY = (p.outH + Cfg::TH - 1) / Cfg::TH;
+    const long long total = (long long)p.N * p.C * p.tilesX * p.tilesY;
+    const long long cap = (long long)n_sm * ctas_per_sm;
+    const int grid = (int)(total < cap ? total : cap);
+    const uintptr_t pa = 2 * sizeof(T) - 1;
+    const int pair_store = ((reinterpret_cast<uintptr_t>(p.y) & pa) == 0 && p.ys[0] % 2 == 0 && p.ys[1] % 2 == 0 && p.ys[2] % 2 == 0) ? 1 : 0;
+    k_upfirdn2d_fast<T, UP, DOWN, F><<<grid, kThreads, Cfg::kSmem, stream>>>(p, total, pair_store);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+}
+
+// returns 1 when the shape is not covered by the fast path (0 / negative: launched / error)
+template <typename T>
+int try_launch_fast(const UpfirdnParams& p, int n_sm, cudaStream_t stream) {
+    if (sizeof(T) > 4) return 1;
+    if (p.xs[3] != 1 || p.ys[3] != 1 || p.fH != 4 || p.fW != 4 || p.upx != p.upy || p.downx != p.downy) return 1;
+    if (p.padx0 % p.upx != 0 || p.pady0 % p.upy != 0) return 1;
+    if ((long long)p.outW * p.downx + 8 > 0x3fffffffll || (long long)p.outH * p.downy + 8 > 0x3fffffffll) return 1;
+    if (p.upx == 1 && p.downx == 1) return launch_fast<T, 1, 1, 4>(p, n_sm, stream);
+    if (p.upx == 2 && p.downx == 1) return launch_fast<T, 2, 1, 4>(p, n_sm, stream);
+    if (p.upx == 1 && p.downx == 2) return launch_fast<T, 1, 2, 4>(p, n_sm, stream);
+    return 1;
+}
+template <> int try_launch_fast<double>(const UpfirdnParams&, int, cudaStream_t) { return 1; }
+
 // ------------------------------------------------------------------------------------------ strided (any layout)
 template <typename T>
 __global__ void __launch_bounds__(kThreads) k_upfirdn2d_strided(const UpfirdnParams p, int c_fastest) {
@@ -144,6 +342,10 @@ int launch_upfirdn2d(UpfirdnParams p, cudaStream_t stream) {
         int dev = 0;
         P3D_CUDA_TRY(cudaGetDevice(&dev));
         P3D_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    {
+        const int rc = try_launch_fast<T>(p, n_sm, stream);
+        if (rc <= 0) return rc;
     }
     // footprint of a 64x16 output tile in input pixels (+1 for the floor of the first index)
     p.inTileW = (kTileW * p.downx + p.fW - 1 + p.upx - 1) / p.upx + 1;

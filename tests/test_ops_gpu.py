@@ -231,6 +231,29 @@ def test_upfirdn2d_large_image_tiles():
         assert (y.cpu() - ref).abs().max().item() < 1e-4
 
 
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.float16, 2e-3), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize('kw', [dict(padding=[1, 1, 1, 1], gain=4.0), dict(up=2, padding=[2, 1, 2, 1], gain=4.0),
+                                dict(down=2, padding=[1, 1, 1, 1]), dict(padding=[-1, 2, 3, -2], flip_filter=True),
+                                dict(up=2, padding=[4, 3, 0, 5], flip_filter=True), dict(down=2, padding=[0, 3, -2, 4])],
+                         ids=['blur', 'up2', 'down2', 'crop_flip', 'up2_asym_flip', 'down2_crop'])
+def test_upfirdn2d_fast_path_misaligned_rows_and_views(kw, dtype, tol):
+    """4x4-filter fast kernel: odd widths (rows not 16-byte aligned), several tiles per image, a non-symmetric 2-D
+    filter (so flip matters), odd storage offsets and row strides (views of a larger buffer)."""
+    up = _up()
+    g = torch.Generator().manual_seed(11)
+    f = torch.rand(4, 4, generator=g) + 0.1
+    big = torch.randn(3, 5, 71, 275, generator=g).to(dtype)
+    big_d = big.to(DEV)
+    for take in (lambda t: t[:, :, :, :273], lambda t: t[:, 1:4, 3:70, 1:274], lambda t: t[:, :, ::2, 5:150]):
+        view, xv = take(big), take(big_d)
+        assert xv.stride(3) == 1 and not xv.is_contiguous()
+        y = up.upfirdn2d(xv, f.to(DEV), **kw)
+        ref = oo.upfirdn2d(view.double(), f.double(), up=kw.get('up', 1), down=kw.get('down', 1), padding=kw['padding'],
+                           flip_filter=kw.get('flip_filter', False), gain=kw.get('gain', 1))
+        assert y.shape == ref.shape and y.dtype == dtype
+        assert (y.cpu().double() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
 # ------------------------------------------------------------------------------------------ filtered_lrelu
 def _fl():
     from panic3d_b200.torch_utils.ops import filtered_lrelu

@@ -381,7 +381,7 @@ def test_ragged_sample_counts_match_oracle(S, Sf, M):
     r.injected_noise = (u_c, u_f)
     with torch.no_grad():
         out = r(planes.to(dev), dec_m.to(dev), ro.to(dev), rd.to(dev), opts)
-    dec = dict(w1=dec_m.net[0].weight.detach(), b1=dec_m.net[0].bias.detach(), w2=dec_m.net[2].weight.detach(), b2=dec_m.net[2].bias.detach())
+    dec = {k: v.detach().cpu() for k, v in dict(w1=dec_m.net[0].weight, b1=dec_m.net[0].bias, w2=dec_m.net[2].weight, b2=dec_m.net[2].bias).items()}
     ref = orc.render(planes, dec, ro, rd, opts, u_c, u_f if Sf > 0 else None, use_triplane=True)
     for o, o_ref in zip(out, ref):
         assert (o.cpu() - o_ref).abs().max().item() < TIGHT
