@@ -48,6 +48,11 @@ def timeit(fn, flush_buf, iters=20, warm=5):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--only', default='', help='substring filter on "op case"')
+    ap.add_argument('--dtypes', default='float16,float32')
+    args = ap.parse_args()
     import panic3d_b200  # noqa: F401
     from panic3d_b200.torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu
     dev = torch.device('cuda:0')
@@ -58,6 +63,8 @@ def main():
     out = []
 
     def rec(op, case, dtype, x_elems, y_elems, fn):
+        if args.only and args.only not in f'{op} {case}':
+            return
         esz = torch.finfo(dtype).bits // 8
         ms = timeit(fn, flush)
         byts = (x_elems + y_elems) * esz
@@ -67,7 +74,7 @@ def main():
         print(json.dumps(r), flush=True)
 
     with torch.no_grad():
-        for dtype in (torch.float16, torch.float32):
+        for dtype in [getattr(torch, d) for d in args.dtypes.split(',')]:
             # a12: lrelu + clamp 256 on conv outputs up to (N,128,512,512) (networks_stylegan2.py:352); linear+clamp ToRGB
             x = torch.randn(4, 128, 512, 512, device=dev, dtype=dtype)
             b = torch.randn(128, device=dev, dtype=dtype)

@@ -43,7 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which('nvcc') or '/usr/local/cuda/bin/nvcc'
     if not os.path.exists(nvcc):
         raise RuntimeError('nvcc not found: cannot build libp3d.so')
-    objdir = os.path.join(os.path.dirname(LIB), 'obj')
+    objdir = os.path.join(PKG, '..', 'gpurun_out', '.obj')        # scratch: neither tracked nor shipped to the GPU box
     os.makedirs(objdir, exist_ok=True)
     headers = glob.glob(os.path.join(CSRC, '*.cuh')) + glob.glob(os.path.join(PKG, '..', 'include', '*.h')) + [os.path.abspath(__file__)]
     t_hdr = max(os.path.getmtime(h) for h in headers)

@@ -102,32 +102,47 @@ __global__ void __launch_bounds__(kThreads) k_upfirdn2d_tiled(const UpfirdnParam
 // ------------------------------------------------------------------------------------------ fast path (4x4 FIR)
 // The shapes panic3d's generator/discriminator hit: a 4x4 [1,3,3,1]^2 filter at (up,down) = (1,1) blur
 // after a transposed conv, (2,1) skip-image upsample, (1,2) discriminator downsample; W-contiguous in and out.
-// Persistent CTAs walk output tiles (128 x 32|16) with a two-stage cp.async pipeline:
-//   * the input footprint of tile i+1 streams into shared memory as ALIGNED 16-byte vectors while tile i is being
-//     computed.  Rows of odd-width images (513 x fp16 = 1026 B) are not 16-byte aligned, so each shared row is
-//     shifted by the row's own misalignment a_r = (address / sizeof(T)) mod VEC: the aligned global vector k of a row
-//     lands on the aligned shared vector k, and element q of the footprint sits at column a_r + q.  Vectors that
-//     straddle the image border (<= 2 per row) are assembled element-wise; rows above/below the image are zeros;
-//   * a thread owns 2 adjacent output columns x RPT consecutive rows.  Every input sample of its window is read from
-//     shared memory ONCE (conflict-free: a warp reads consecutive elements of one row) and scattered into the
-//     accumulators of the outputs it feeds - tap indices ky = sr*UP - r*DOWN, kx = sc*UP - e*DOWN are compile-time,
-//     so the polyphase structure (up=2 visits 2x2 of the 4x4 taps per output) costs nothing and the 16 taps live
-//     in registers;
-//   * fp32 accumulation for every storage type, one rounding at the store (as the reference's scalar_t=float path).
+// With 16 fp32 FMAs per output the op sits at the instruction-issue limit long before HBM (16 x 134 M outputs is
+// already 60 us of FMA-pipe time against an 82 us HBM floor for fp16), so the kernel is built to minimise issued
+// instructions per output as much as bytes:
+//   * persistent CTAs walk output tiles (128 x 8*RPT) with a two-stage cp.async pipeline: the input footprint of
+//     tile i+1 streams into shared memory as ALIGNED 16-byte vectors while tile i is computed.  Rows of odd-width
+//     images (513 x fp16 = 1026 B) are not 16-byte aligned, so each shared row is shifted by the row's own
+//     misalignment a_r = (address / sizeof(T)) mod VEC: aligned global vector k of a row lands on aligned shared
+//     vector k, and footprint element q sits at column a_r + q.  Vectors that straddle the image border (<= 2 per
+//     row) are assembled element-wise, rows above/below the image are zeros.  Row base pointers are computed once
+//     per tile (one thread per row, one tile ahead), so a vector costs ~15 instructions to issue;
+//   * a thread owns 4 output columns x RPT consecutive rows: up = 1 -> one column in each of four 32-column blocks,
+//     up = 2 -> an (even, odd) phase pair in each of two 64-column blocks.  Lanes of a warp therefore read
+//     consecutive shared-memory elements (no bank conflicts; the first version's 4 adjacent columns per thread cost
+//     4-way conflicts in fp32).  Every input sample of the window is read once and scattered into the accumulators
+//     it feeds; tap indices are compile-time (ky = sr*UP - r*DOWN, kx from the polyphase slot), the taps sit in
+//     uniform registers, and the FMAs are issued as packed fma.rn.f32x2 (two outputs per instruction);
+//   * fp32 accumulation for every storage type, one rounding at the store (the reference's scalar_t=float path).
 template <typename T, int UP, int DOWN, int F>
 struct FastCfg {
     static constexpr int VEC = 16 / (int)sizeof(T);
-    static constexpr int TW = 128;
-    static constexpr int RPT = (DOWN == 1) ? 8 : 4;
-    static constexpr int TH = 4 * RPT;
+    static constexpr int EPT = 4;                                  // outputs per thread and row:
+    static constexpr int EA = UP;                                  //   EA adjacent columns (an even/odd phase pair when up = 2)
+    static constexpr int NB = EPT / EA;                            //   in NB blocks, BS columns apart - so a warp reads
+    static constexpr int TW = 32 * EPT;                            //   consecutive shared-memory words (no bank conflicts)
+    static constexpr int BS = TW / NB;
+    static constexpr int RPT = (DOWN == 1) ? 8 : (sizeof(T) == 4 ? 2 : 4);
+    static constexpr int TH = 8 * RPT;
     static constexpr int IN_W = ((TW - 1) * DOWN + F - 1) / UP + 1;
     static constexpr int IN_H = ((TH - 1) * DOWN + F - 1) / UP + 1;
-    static constexpr int NIN = (DOWN + F - 1) / UP + 1;
+    static constexpr int NIN = ((EA - 1) * DOWN + F - 1) / UP + 1;             // input columns per block a thread touches per row
     static constexpr int NINROWS = ((RPT - 1) * DOWN + F - 1) / UP + 1;
+    static constexpr int NT = (F + UP - 1) / UP;                   // taps per output per dimension (polyphase slots)
+    static constexpr int KX_ODD = ((-DOWN) % UP + UP) % UP;        // first tap of an odd output column
     static constexpr int PITCH = (IN_W + VEC - 1 + VEC - 1) / VEC * VEC;
     static constexpr int NV = PITCH / VEC;
     static constexpr size_t kBufBytes = (size_t)IN_H * PITCH * sizeof(T);
-    static constexpr size_t kSmem = 2 * kBufBytes + 2 * IN_H * sizeof(int);
+    static constexpr size_t kRowPtrOff = 2 * kBufBytes;
+    static constexpr size_t kShiftOff = kRowPtrOff + 2 * IN_H * sizeof(void*);
+    static constexpr size_t kSmem = kShiftOff + 2 * IN_H * sizeof(int);
+    static_assert(F % UP == 0 && (UP == 1 || UP == 2) && (UP == 1 || DOWN == 1), "polyphase slots must be uniform");
+    static_assert(IN_H <= 256, "one thread per footprint row");
 };
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
@@ -137,50 +152,84 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <typename T, int UP, int DOWN, int F>
-__global__ void __launch_bounds__(kThreads) k_upfirdn2d_fast(const UpfirdnParams p, long long total_tiles, int pair_store) {
+__global__ void __launch_bounds__(kThreads) k_upfirdn2d_fast(const UpfirdnParams p, unsigned total_tiles, int vec_store) {
     using Cfg = FastCfg<T, UP, DOWN, F>;
     using V = uint4;
-    constexpr int VEC = Cfg::VEC, PITCH = Cfg::PITCH, NV = Cfg::NV, IN_H = Cfg::IN_H, RPT = Cfg::RPT;
+    constexpr int VEC = Cfg::VEC, PITCH = Cfg::PITCH, NV = Cfg::NV, IN_H = Cfg::IN_H, RPT = Cfg::RPT, NT = Cfg::NT, EPT = Cfg::EPT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_buf[2] = {reinterpret_cast<T*>(smem_raw), reinterpret_cast<T*>(smem_raw + Cfg::kBufBytes)};
-    int* s_a = reinterpret_cast<int*>(smem_raw + 2 * Cfg::kBufBytes);           // [2][IN_H] row shifts
+    constexpr int kBufElems = (int)(Cfg::kBufBytes / sizeof(T));
+    T* const s_x = reinterpret_cast<T*>(smem_raw);                              // [2][IN_H][PITCH]; index arithmetic only,
+                                                                                // so every access stays an LDS/STS
+    const T** const s_rowp = reinterpret_cast<const T**>(smem_raw + Cfg::kRowPtrOff);   // [2][IN_H] footprint row bases
+    int* const s_a = reinterpret_cast<int*>(smem_raw + Cfg::kShiftOff);                 // [2][IN_H] row shifts
     const int tid = threadIdx.x;
     const T* xp = reinterpret_cast<const T*>(p.x);
     T* yp = reinterpret_cast<T*>(p.y);
 
-    float w[F * F];
+    // taps as (even column, odd column) pairs per polyphase slot: w2[ky][j] = (w[ky][j*UP], w[ky][KX_ODD + j*UP])
+    float2 w2[F][NT];
 #pragma unroll
-    for (int i = 0; i < F * F; ++i) {
-        const int ky = i / F, kx = i % F;
-        const int sy = p.flip ? ky : F - 1 - ky, sx = p.flip ? kx : F - 1 - kx;
-        w[i] = p.f[sy * p.fsh + sx * p.fsw] * p.gain;
+    for (int ky = 0; ky < F; ++ky) {
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+            const int kxe = j * UP, kxo = Cfg::KX_ODD + j * UP;
+            const int sy = p.flip ? ky : F - 1 - ky;
+            const int sxe = p.flip ? kxe : F - 1 - kxe, sxo = p.flip ? kxo : F - 1 - kxo;
+            w2[ky][j] = make_float2(p.f[sy * p.fsh + sxe * p.fsw] * p.gain, p.f[sy * p.fsh + sxo * p.fsw] * p.gain);
+        }
     }
-    const long long tiles_per_img = (long long)p.tilesX * p.tilesY;
+    const unsigned tiles_per_img = (unsigned)(p.tilesX * p.tilesY);
 
-    auto issue = [&](long long t, int b) {
-        const long long img = t / tiles_per_img;
-        const int rem = (int)(t - img * tiles_per_img);
-        const int tyi = rem / p.tilesX, txi = rem - tyi * p.tilesX;
-        const int n = (int)(img / p.C), c = (int)(img - (long long)n * p.C);
-        const int ix0 = (txi * Cfg::TW * DOWN - p.padx0) / UP, iy0 = (tyi * Cfg::TH * DOWN - p.pady0) / UP;   // exact
-        const T* xi = xp + n * p.xs[0] + c * p.xs[1];
-        T* sb = s_buf[b];
+    // tile walk: t -> (txi, tyi, c, n) advances by gridDim.x per iteration; the mixed-radix increment is decomposed
+    // once, so stepping costs a few adds/compares instead of four integer divisions per tile
+    struct Tile { int txi, tyi, c, n; const T* xi; long long yoff; };
+    int d_x, d_y, d_c, d_n;
+    {
+        unsigned g = gridDim.x;
+        d_x = (int)(g % (unsigned)p.tilesX); g /= (unsigned)p.tilesX;
+        d_y = (int)(g % (unsigned)p.tilesY); g /= (unsigned)p.tilesY;
+        d_c = (int)(g % (unsigned)p.C); d_n = (int)(g / (unsigned)p.C);
+    }
+    auto locate = [&](Tile& tl) { tl.xi = xp + tl.n * p.xs[0] + tl.c * p.xs[1]; tl.yoff = tl.n * p.ys[0] + tl.c * p.ys[1]; };
+    auto decode = [&](unsigned t) {
+        const unsigned img = t / tiles_per_img;
+        const unsigned rem = t - img * tiles_per_img;
+        Tile tl;
+        tl.tyi = (int)(rem / (unsigned)p.tilesX); tl.txi = (int)(rem - (unsigned)tl.tyi * (unsigned)p.tilesX);
+        tl.n = (int)(img / (unsigned)p.C); tl.c = (int)(img - (unsigned)tl.n * (unsigned)p.C);
+        locate(tl);
+        return tl;
+    };
+    auto advance = [&](Tile tl) {                                             // tile index + gridDim.x
+        tl.txi += d_x; int carry = tl.txi >= p.tilesX; tl.txi -= carry ? p.tilesX : 0;
+        tl.tyi += d_y + carry; carry = tl.tyi >= p.tilesY; tl.tyi -= carry ? p.tilesY : 0;
+        tl.c += d_c + carry; carry = tl.c >= p.C; tl.c -= carry ? p.C : 0;
+        tl.n += d_n + carry;
+        locate(tl);
+        return tl;
+    };
+    // footprint row bases of a tile (element q = 0 of each row; nullptr for rows above/below the image)
+    auto rows = [&](const Tile& tl, int slot) {
+        if (tid < IN_H) {
+            const int ix0 = (tl.txi * Cfg::TW * DOWN - p.padx0) / UP, iy = (tl.tyi * Cfg::TH * DOWN - p.pady0) / UP + tid;   // exact
+            s_rowp[slot * IN_H + tid] = (iy >= 0 && iy < p.inH) ? tl.xi + (long long)iy * p.xs[2] + ix0 : nullptr;
+        }
+    };
+    auto issue = [&](const Tile& tl, int slot) {
+        const int ix0 = (tl.txi * Cfg::TW * DOWN - p.padx0) / UP;
+        T* sb = s_x + slot * kBufElems;
         for (int i = tid; i < IN_H * NV; i += kThreads) {
             const int r = i / NV, k = i - r * NV;
-            const int iy = iy0 + r;
-            V* dst = reinterpret_cast<V*>(sb + r * PITCH + k * VEC);
-            if (iy < 0 || iy >= p.inH) {
-                *dst = make_uint4(0u, 0u, 0u, 0u);
-                if (k == 0) s_a[b * IN_H + r] = 0;
-                continue;
-            }
-            const T* row0 = xi + (long long)iy * p.xs[2] + ix0;              // footprint element q = 0 (may be outside the row)
+            V* dst = reinterpret_cast<V*>(sb + i * VEC);                     // == sb + r*PITCH + k*VEC
+            const T* row0 = s_rowp[slot * IN_H + r];
             const int a = (int)((reinterpret_cast<uintptr_t>(row0) / sizeof(T)) & (VEC - 1));
-            if (k == 0) s_a[b * IN_H + r] = a;
+            if (k == 0) s_a[slot * IN_H + r] = a;
             const int ix = ix0 + k * VEC - a;                                // image column of the vector's first element
             const T* src = row0 + (k * VEC - a);                             // 16-byte aligned
-            if (ix >= 0 && ix + VEC <= p.inW) {
+            if (row0 != nullptr && ix >= 0 && ix + VEC <= p.inW) {
                 cp_async16(dst, src);
+            } else if (row0 == nullptr || ix + VEC <= 0 || ix >= p.inW) {
+                *dst = make_uint4(0u, 0u, 0u, 0u);
             } else {
                 alignas(16) T tmp[VEC];
 #pragma unroll
@@ -190,74 +239,95 @@ __global__ void __launch_bounds__(kThreads) k_upfirdn2d_fast(const UpfirdnParams
         }
     };
 
-    long long t = blockIdx.x;
+    unsigned t = blockIdx.x;
     if (t >= total_tiles) return;
-    issue(t, 0);
+    Tile cur = decode(t);
+    rows(cur, 0);
+    Tile nxt = cur;
+    if (t + gridDim.x < total_tiles) { nxt = advance(cur); rows(nxt, 1); }
+    __syncthreads();
+    issue(cur, 0);
     cp_async_commit();
-    const int tx = tid & 63, tr = tid >> 6;
-    const int x0 = 2 * tx, y0 = tr * RPT;
-    const int bx = (x0 * DOWN) / UP, by = (y0 * DOWN) / UP;
+    const int tx = tid & 31, tr = tid >> 5;
+    constexpr int EA = Cfg::EA, NB = Cfg::NB, BS = Cfg::BS;
+    const int y0 = tr * RPT, by = (y0 * DOWN) / UP;
+    int bxm[NB];                                                             // first footprint column of each block
+#pragma unroll
+    for (int m = 0; m < NB; ++m) bxm[m] = ((m * BS + EA * tx) * DOWN) / UP;  // exact: EA*tx and BS are multiples of UP
     int b = 0;
     for (; t < total_tiles; t += gridDim.x, b ^= 1) {
-        const long long tn = t + gridDim.x;
-        if (tn < total_tiles) issue(tn, b ^ 1);
+        const bool has_next = t + gridDim.x < total_tiles;
+        if (has_next) issue(nxt, b ^ 1);                                     // row bases of nxt were published one sync ago
         cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
+        // row bases for the tile after next go into the slot `cur` used (its issue finished an iteration ago)
+        Tile nn = nxt;
+        if (t + 2ull * gridDim.x < total_tiles) { nn = advance(nxt); rows(nn, b); }
 
-        float acc[RPT][2];
+        // acc[r][q]: up = 1 -> columns (block 2q, block 2q+1) at tx; up = 2 -> columns (2tx, 2tx+1) of block q
+        float2 acc[RPT][EPT / 2];
 #pragma unroll
-        for (int r = 0; r < RPT; ++r) acc[r][0] = acc[r][1] = 0.f;
-        const T* sb = s_buf[b];
+        for (int r = 0; r < RPT; ++r) acc[r][0] = acc[r][1] = make_float2(0.f, 0.f);
+        const T* sb = s_x + b * kBufElems;
 #pragma unroll
         for (int sr = 0; sr < Cfg::NINROWS; ++sr) {
-            const T* rowp = sb + (by + sr) * PITCH + s_a[b * IN_H + by + sr] + bx;
-            float v[Cfg::NIN];
+            const T* rowp = sb + (by + sr) * PITCH + s_a[b * IN_H + by + sr];
+            float v[NB][Cfg::NIN];
 #pragma unroll
-            for (int sc = 0; sc < Cfg::NIN; ++sc) v[sc] = Px<T>::ld(rowp[sc]);
+            for (int m = 0; m < NB; ++m) {
+#pragma unroll
+                for (int sc = 0; sc < Cfg::NIN; ++sc) v[m][sc] = Px<T>::ld(rowp[bxm[m] + sc]);
+            }
 #pragma unroll
             for (int r = 0; r < RPT; ++r) {
                 const int ky = sr * UP - r * DOWN;
                 if (ky < 0 || ky >= F) continue;
 #pragma unroll
-                for (int e = 0; e < 2; ++e) {
+                for (int q = 0; q < EPT / 2; ++q) {
 #pragma unroll
-                    for (int sc = 0; sc < Cfg::NIN; ++sc) {
-                        const int kx = sc * UP - e * DOWN;
-                        if (kx < 0 || kx >= F) continue;
-                        acc[r][e] = fmaf(v[sc], w[ky * F + kx], acc[r][e]);
+                    for (int j = 0; j < NT; ++j) {
+                        if (UP == 1) {                                       // same tap j, two blocks
+                            acc[r][q] = __ffma2_rn(make_float2(v[(2 * q) % NB][j], v[(2 * q + 1) % NB][j]), w2[ky][j], acc[r][q]);
+                        } else {                                             // even column: tap 2j, input j; odd: tap KX_ODD+2j
+                            constexpr int dummy = 0; (void)dummy;
+                            const int sco = (DOWN + Cfg::KX_ODD + j * UP) / UP;
+                            acc[r][q] = __ffma2_rn(make_float2(v[q % NB][j], v[q % NB][sco]), w2[ky][j], acc[r][q]);
+                        }
                     }
                 }
             }
         }
         {
-            const long long img = t / tiles_per_img;
-            const int rem = (int)(t - img * tiles_per_img);
-            const int tyi = rem / p.tilesX, txi = rem - tyi * p.tilesX;
-            const int n = (int)(img / p.C), c = (int)(img - (long long)n * p.C);
-            const int ox = txi * Cfg::TW + x0, oy0 = tyi * Cfg::TH + y0;
-            T* yi = yp + n * p.ys[0] + c * p.ys[1] + ox;
-            if (ox < p.outW) {
+            const int oxb = cur.txi * Cfg::TW + EA * tx, oy0 = cur.tyi * Cfg::TH + y0;
+            T* yi = yp + cur.yoff + oxb;
 #pragma unroll
-                for (int r = 0; r < RPT; ++r) {
-                    const int oy = oy0 + r;
-                    if (oy >= p.outH) break;
-                    T* dst = yi + (long long)oy * p.ys[2];
-                    if (ox + 1 < p.outW) {
-                        if (pair_store) {
+            for (int r = 0; r < RPT; ++r) {
+                const int oy = oy0 + r;
+                if (oy >= p.outH) break;
+                T* dst = yi + (long long)oy * p.ys[2];
+                if (UP == 1) {
+#pragma unroll
+                    for (int m = 0; m < NB; ++m)
+                        if (oxb + m * BS < p.outW) dst[m * BS] = Px<T>::st((m & 1) ? acc[r][m / 2].y : acc[r][m / 2].x);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < EPT / 2; ++q) {
+                        const int ox = oxb + q * BS;
+                        if (vec_store && ox + 1 < p.outW) {
                             struct alignas(2 * sizeof(T)) Pair { T a, b; };
-                            *reinterpret_cast<Pair*>(dst) = Pair{Px<T>::st(acc[r][0]), Px<T>::st(acc[r][1])};
+                            *reinterpret_cast<Pair*>(dst + q * BS) = Pair{Px<T>::st(acc[r][q].x), Px<T>::st(acc[r][q].y)};
                         } else {
-                            dst[0] = Px<T>::st(acc[r][0]);
-                            dst[1] = Px<T>::st(acc[r][1]);
+                            if (ox < p.outW) dst[q * BS] = Px<T>::st(acc[r][q].x);
+                            if (ox + 1 < p.outW) dst[q * BS + 1] = Px<T>::st(acc[r][q].y);
                         }
-                    } else {
-                        dst[0] = Px<T>::st(acc[r][0]);
                     }
                 }
             }
         }
-        __syncthreads();                                                     // buffer b is free for the prefetch after next
+        __syncthreads();                                                     // buffer b and row slot b^1 are free again
+        cur = nxt;
+        nxt = nn;
     }
     cp_async_wait<0>();
 }
@@ -274,11 +344,12 @@ int launch_fast(UpfirdnParams p, int n_sm, cudaStream_t stream) {
     p.tilesX = (p.outW + Cfg::TW - 1) / Cfg::TW;
     p.tilesY = (p.outH + Cfg::TH - 1) / Cfg::TH;
     const long long total = (long long)p.N * p.C * p.tilesX * p.tilesY;
+    if (total >= 0x7fffffffll) return 1;                          // tile counter is 32-bit: leave it to the generic kernel
     const long long cap = (long long)n_sm * ctas_per_sm;
     const int grid = (int)(total < cap ? total : cap);
     const uintptr_t pa = 2 * sizeof(T) - 1;
     const int pair_store = ((reinterpret_cast<uintptr_t>(p.y) & pa) == 0 && p.ys[0] % 2 == 0 && p.ys[1] % 2 == 0 && p.ys[2] % 2 == 0) ? 1 : 0;
-    k_upfirdn2d_fast<T, UP, DOWN, F><<<grid, kThreads, Cfg::kSmem, stream>>>(p, total, pair_store);
+    k_upfirdn2d_fast<T, UP, DOWN, F><<<grid, kThreads, Cfg::kSmem, stream>>>(p, (unsigned)total, pair_store);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }
