@@ -192,13 +192,32 @@ __global__ void k_raygen_ortho(const float* __restrict__ rot, const float* __res
     }
 }
 
+// pairs[2*(i+1)], pairs[2*(i+1)+1] = (min, max) of view i  ->  pairs[0], pairs[1] = batch-wide (min, max)
+__global__ void k_merge_bounds(float* pairs, int n) {
+    float lo = INFINITY, hi = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += 32) { lo = fminf(lo, pairs[2 * (i + 1)]); hi = fmaxf(hi, pairs[2 * (i + 1) + 1]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+    if (threadIdx.x == 0) { pairs[0] = lo; pairs[1] = hi; }
+}
+
 // ------------------------------------------------------------------------------------------
 // host arena for the *_host entry point
 // ------------------------------------------------------------------------------------------
 struct Arena {
     std::mutex mu;
     std::vector<std::pair<void*, size_t>> bufs;   // slot -> (ptr, bytes)
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_in = nullptr, copy_out = nullptr;
+    std::vector<cudaEvent_t> events;
+    int event(size_t i, cudaEvent_t* out) {
+        while (events.size() <= i) {
+            cudaEvent_t e;
+            P3D_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            events.push_back(e);
+        }
+        *out = events[i];
+        return P3D_OK;
+    }
     int get(size_t slot, size_t bytes, void** out) {
         if (bufs.size() <= slot) bufs.resize(slot + 1, {nullptr, 0});
         if (bufs[slot].second < bytes) {
@@ -213,7 +232,11 @@ struct Arena {
     void release() {
         for (auto& b : bufs) if (b.first) cudaFree(b.first);
         bufs.clear();
+        for (auto& e : events) cudaEventDestroy(e);
+        events.clear();
         if (stream) { cudaStreamDestroy(stream); stream = nullptr; }
+        if (copy_in) { cudaStreamDestroy(copy_in); copy_in = nullptr; }
+        if (copy_out) { cudaStreamDestroy(copy_out); copy_out = nullptr; }
     }
 };
 static Arena g_arena;
@@ -380,21 +403,33 @@ int p3d_render_forward_host(const p3d_render_params* p_in, const float* planes_n
                             const float* w2, const float* b2, const float* cam2world, const float* intrinsics,
                             int32_t resolution, const float* u_coarse, const float* u_fine, float* out_rgb,
                             float* out_depth, float* out_wsum, float* out_xyz) {
+    // Host-resident inputs -> host-resident outputs.  The step is PCIe-bound (a view's tri-planes are 100 MB of
+    // fp32 against ~1 ms of rendering), so views are pipelined over three streams: H2D of view v+1 overlaps layout +
+    // rendering of view v, whose rgb / weights / xyz start their D2H while view v+1 renders.  Each view is one
+    // p3d_render_forward call with defer_depth_clamp; the batch-wide depth clamp (ray_marcher.py:50) is applied once
+    // at the end from the merged per-view bounds, so results equal the one-shot call on the whole batch.
     P3D_REQUIRE(p_in && planes_nchw && w1 && b1 && w2 && b2 && cam2world && intrinsics, "null input pointer");
     P3D_REQUIRE(out_rgb && out_depth && out_wsum && out_xyz, "null output pointer");
     p3d_render_params p = *p_in;
     P3D_REQUIRE(p.n_rays == resolution * resolution, "n_rays must equal resolution^2");
+    P3D_REQUIRE(p.n_views >= 0, "bad sizes");
+    if ((long long)p.n_views * p.n_rays == 0) return P3D_OK;
     std::lock_guard<std::mutex> lock(g_arena.mu);
     if (!g_arena.stream) P3D_CUDA_TRY(cudaStreamCreateWithFlags(&g_arena.stream, cudaStreamNonBlocking));
-    cudaStream_t st = g_arena.stream;
+    if (!g_arena.copy_in) P3D_CUDA_TRY(cudaStreamCreateWithFlags(&g_arena.copy_in, cudaStreamNonBlocking));
+    if (!g_arena.copy_out) P3D_CUDA_TRY(cudaStreamCreateWithFlags(&g_arena.copy_out, cudaStreamNonBlocking));
+    cudaStream_t st = g_arena.stream, sin = g_arena.copy_in, sout = g_arena.copy_out;
     const size_t N = p.n_views, M = p.n_rays, C = p.channels, HW = (size_t)p.plane_h * p.plane_w;
-    const size_t plane_elems = N * 3 * C * HW;
+    const size_t view_elems = 3 * C * HW;
     const size_t esz = p.planes_bf16 ? 2 : 4;
     p.stride_col = C; p.stride_row = (int64_t)p.plane_w * C; p.stride_plane = (int64_t)HW * C; p.stride_view = 3 * p.stride_plane;
-    void *d_nchw, *d_cl, *d_w, *d_cam, *d_rays, *d_u, *d_out, *d_ws;
+    p3d_render_params pv = p;                      // one view per launch
+    pv.n_views = 1;
+    pv.defer_depth_clamp = 1;
+    void *d_nchw, *d_cl, *d_w, *d_cam, *d_rays, *d_u, *d_out, *d_ws, *d_bounds;
     int rc;
-    if ((rc = g_arena.get(0, plane_elems * 4, &d_nchw))) return rc;
-    if ((rc = g_arena.get(1, plane_elems * esz, &d_cl))) return rc;
+    if ((rc = g_arena.get(0, N * view_elems * 4, &d_nchw))) return rc;
+    if ((rc = g_arena.get(1, N * view_elems * esz, &d_cl))) return rc;
     const size_t nw = (size_t)p.hidden * C + p.hidden + (size_t)p.out_dim * p.hidden + p.out_dim;
     if ((rc = g_arena.get(2, nw * 4, &d_w))) return rc;
     if ((rc = g_arena.get(3, N * 25 * 4, &d_cam))) return rc;
@@ -403,30 +438,56 @@ int p3d_render_forward_host(const p3d_render_params* p_in, const float* planes_n
     if ((rc = g_arena.get(5, (nu + 1) * 4, &d_u))) return rc;
     const size_t out_per_ray = (size_t)(p.out_dim - 1) + 1 + 1 + 3;
     if ((rc = g_arena.get(6, N * M * out_per_ray * 4, &d_out))) return rc;
-    const size_t ws_bytes = p3d_render_workspace_bytes(&p);
+    const size_t ws_bytes = p3d_render_workspace_bytes(&pv);
     if ((rc = g_arena.get(7, ws_bytes, &d_ws))) return rc;
+    if ((rc = g_arena.get(8, (N + 1) * 2 * 4, &d_bounds))) return rc;
 
+    cudaEvent_t ev_small, ev_rays;
+    if ((rc = g_arena.event(0, &ev_small)) || (rc = g_arena.event(1, &ev_rays))) return rc;
     float* dw1 = (float*)d_w; float* db1 = dw1 + (size_t)p.hidden * C; float* dw2 = db1 + p.hidden; float* db2 = dw2 + (size_t)p.out_dim * p.hidden;
-    P3D_CUDA_TRY(cudaMemcpyAsync(d_nchw, planes_nchw, plane_elems * 4, cudaMemcpyHostToDevice, st));
-    P3D_CUDA_TRY(cudaMemcpyAsync(dw1, w1, (size_t)p.hidden * C * 4, cudaMemcpyHostToDevice, st));
-    P3D_CUDA_TRY(cudaMemcpyAsync(db1, b1, (size_t)p.hidden * 4, cudaMemcpyHostToDevice, st));
-    P3D_CUDA_TRY(cudaMemcpyAsync(dw2, w2, (size_t)p.out_dim * p.hidden * 4, cudaMemcpyHostToDevice, st));
-    P3D_CUDA_TRY(cudaMemcpyAsync(db2, b2, (size_t)p.out_dim * 4, cudaMemcpyHostToDevice, st));
+    P3D_CUDA_TRY(cudaMemcpyAsync(dw1, w1, (size_t)p.hidden * C * 4, cudaMemcpyHostToDevice, sin));
+    P3D_CUDA_TRY(cudaMemcpyAsync(db1, b1, (size_t)p.hidden * 4, cudaMemcpyHostToDevice, sin));
+    P3D_CUDA_TRY(cudaMemcpyAsync(dw2, w2, (size_t)p.out_dim * p.hidden * 4, cudaMemcpyHostToDevice, sin));
+    P3D_CUDA_TRY(cudaMemcpyAsync(db2, b2, (size_t)p.out_dim * 4, cudaMemcpyHostToDevice, sin));
     float* dc2w = (float*)d_cam; float* dK = dc2w + N * 16;
-    P3D_CUDA_TRY(cudaMemcpyAsync(dc2w, cam2world, N * 16 * 4, cudaMemcpyHostToDevice, st));
-    P3D_CUDA_TRY(cudaMemcpyAsync(dK, intrinsics, N * 9 * 4, cudaMemcpyHostToDevice, st));
-    float *duc = nullptr, *duf = nullptr;
-    if (u_coarse) { duc = (float*)d_u; P3D_CUDA_TRY(cudaMemcpyAsync(duc, u_coarse, N * M * p.n_coarse * 4, cudaMemcpyHostToDevice, st)); }
-    if (u_fine) { duf = (float*)d_u + (u_coarse ? N * M * p.n_coarse : 0); P3D_CUDA_TRY(cudaMemcpyAsync(duf, u_fine, N * M * p.n_fine * 4, cudaMemcpyHostToDevice, st)); }
-    if ((rc = p3d_planes_to_channels_last((const float*)d_nchw, d_cl, (int64_t)N * 3, p.channels, p.plane_h, p.plane_w, p.planes_bf16, st))) return rc;
+    P3D_CUDA_TRY(cudaMemcpyAsync(dc2w, cam2world, N * 16 * 4, cudaMemcpyHostToDevice, sin));
+    P3D_CUDA_TRY(cudaMemcpyAsync(dK, intrinsics, N * 9 * 4, cudaMemcpyHostToDevice, sin));
+    P3D_CUDA_TRY(cudaEventRecord(ev_small, sin));
+    P3D_CUDA_TRY(cudaStreamWaitEvent(st, ev_small, 0));
     float* dro = (float*)d_rays; float* drd = dro + N * M * 3;
     if ((rc = p3d_raygen_pinhole(dc2w, dK, p.n_views, resolution, dro, drd, st))) return rc;
+    float* duc_all = u_coarse ? (float*)d_u : nullptr;
+    float* duf_all = u_fine ? (float*)d_u + (u_coarse ? N * M * p.n_coarse : 0) : nullptr;
     float* drgb = (float*)d_out; float* ddepth = drgb + N * M * (p.out_dim - 1); float* dwsum = ddepth + N * M; float* dxyz = dwsum + N * M;
-    if ((rc = p3d_render_forward(&p, d_cl, dw1, db1, dw2, db2, dro, drd, duc, duf, d_ws, ws_bytes, drgb, ddepth, dwsum, dxyz, st))) return rc;
-    P3D_CUDA_TRY(cudaMemcpyAsync(out_rgb, drgb, N * M * (p.out_dim - 1) * 4, cudaMemcpyDeviceToHost, st));
+    float* dbounds = (float*)d_bounds;
+    const size_t rgb_v = M * (size_t)(p.out_dim - 1);
+    for (size_t v = 0; v < N; ++v) {
+        cudaEvent_t ev_in, ev_done;
+        if ((rc = g_arena.event(2 + 2 * v, &ev_in)) || (rc = g_arena.event(3 + 2 * v, &ev_done))) return rc;
+        float* nchw_v = (float*)d_nchw + v * view_elems;
+        P3D_CUDA_TRY(cudaMemcpyAsync(nchw_v, planes_nchw + v * view_elems, view_elems * 4, cudaMemcpyHostToDevice, sin));
+        float *duc = nullptr, *duf = nullptr;
+        if (u_coarse) { duc = duc_all + v * M * p.n_coarse; P3D_CUDA_TRY(cudaMemcpyAsync(duc, u_coarse + v * M * p.n_coarse, M * p.n_coarse * 4, cudaMemcpyHostToDevice, sin)); }
+        if (u_fine) { duf = duf_all + v * M * p.n_fine; P3D_CUDA_TRY(cudaMemcpyAsync(duf, u_fine + v * M * p.n_fine, M * p.n_fine * 4, cudaMemcpyHostToDevice, sin)); }
+        P3D_CUDA_TRY(cudaEventRecord(ev_in, sin));
+        P3D_CUDA_TRY(cudaStreamWaitEvent(st, ev_in, 0));
+        void* cl_v = (char*)d_cl + v * view_elems * esz;
+        if ((rc = p3d_planes_to_channels_last(nchw_v, cl_v, 3, p.channels, p.plane_h, p.plane_w, p.planes_bf16, st))) return rc;
+        pv.seed = p.seed + v * 0x9E3779B97F4A7C15ull;          // independent Philox stream per view (used when u_* are NULL)
+        if ((rc = p3d_render_forward(&pv, cl_v, dw1, db1, dw2, db2, dro + v * M * 3, drd + v * M * 3, duc, duf, d_ws, ws_bytes,
+                                     drgb + v * rgb_v, ddepth + v * M, dwsum + v * M, dxyz + v * M * 3, st))) return rc;
+        if ((rc = p3d_render_depth_bounds(d_ws, dbounds + 2 * (v + 1), st))) return rc;
+        P3D_CUDA_TRY(cudaEventRecord(ev_done, st));
+        P3D_CUDA_TRY(cudaStreamWaitEvent(sout, ev_done, 0));
+        P3D_CUDA_TRY(cudaMemcpyAsync(out_rgb + v * rgb_v, drgb + v * rgb_v, rgb_v * 4, cudaMemcpyDeviceToHost, sout));
+        P3D_CUDA_TRY(cudaMemcpyAsync(out_wsum + v * M, dwsum + v * M, M * 4, cudaMemcpyDeviceToHost, sout));
+        P3D_CUDA_TRY(cudaMemcpyAsync(out_xyz + v * M * 3, dxyz + v * M * 3, M * 3 * 4, cudaMemcpyDeviceToHost, sout));
+    }
+    k_merge_bounds<<<1, 32, 0, st>>>(dbounds, (int)N);
+    P3D_LAUNCH_CHECK();
+    if ((rc = p3d_depth_finalize(ddepth, (int64_t)(N * M), dbounds, st))) return rc;
     P3D_CUDA_TRY(cudaMemcpyAsync(out_depth, ddepth, N * M * 4, cudaMemcpyDeviceToHost, st));
-    P3D_CUDA_TRY(cudaMemcpyAsync(out_wsum, dwsum, N * M * 4, cudaMemcpyDeviceToHost, st));
-    P3D_CUDA_TRY(cudaMemcpyAsync(out_xyz, dxyz, N * M * 3 * 4, cudaMemcpyDeviceToHost, st));
+    P3D_CUDA_TRY(cudaStreamSynchronize(sout));
     P3D_CUDA_TRY(cudaStreamSynchronize(st));
     return P3D_OK;
 }

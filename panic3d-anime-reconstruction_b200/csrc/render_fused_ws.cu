@@ -588,6 +588,12 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             tc_fence_after();
             const int grp = (int)blockIdx.x + n * (int)gridDim.x;
             const long long ray0 = (long long)grp * GR;
+            // A warp's 32 TMEM rows are the same ray(s) in each of its three tiles, so the per-tile column sums are
+            // first added up in a register and published once: every (ray, channel) cell of sl.acc then receives
+            // exactly two shared-memory adds (one per chunk), whose order cannot change the rounded sum - the kernel
+            // is bit-reproducible run to run and independent of how the rays are batched.
+            float part[2] = {0.f, 0.f};
+            const int rl_first = (quarter * 32) / RPT;
             for (int i = 0; i < 3; ++i) {
                 const int tile6 = chunk + 2 * i;                           // this warp's tiles: {0,2,4} or {1,3,5}
                 const int pass = tile6 / 3, k = tile6 - pass * 3;
@@ -600,8 +606,9 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
                 tmem_ld32(tmem + kColD2 + (slot_i * 6 + tile6) * 32 + lane_base, v);
 #pragma unroll
                 for (int c = 0; c < kRgb; ++c) v[c] = fmaf(rcp_approx(1.f + ex2_approx(v[c] + sm.b2c[c])), ca, cb);
-                const int rl_lo = __shfl_sync(0xffffffffu, rl, 0), rl_hi = __shfl_sync(0xffffffffu, rl, 31);
-                for (int target = rl_lo; target <= rl_hi; ++target) {
+#pragma unroll
+                for (int t2 = 0; t2 < 32 / RPT; ++t2) {
+                    const int target = rl_first + t2;
                     float r[32];
 #pragma unroll
                     for (int c = 0; c < 32; ++c) r[c] = (RPT == 32 || rl == target) ? v[c] : 0.f;
@@ -615,9 +622,11 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
                             r[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                         }
                     }
-                    atomicAdd(&sl.acc[target][lane], r[0]);
+                    part[t2] += r[0];
                 }
             }
+#pragma unroll
+            for (int t2 = 0; t2 < 32 / RPT; ++t2) atomicAdd(&sl.acc[rl_first + t2][lane], part[t2]);
             tc_fence_before();
             asm volatile("bar.sync 1, 256;" ::: "memory");                 // all eight epilogue warps
             if (etid < GR * kRgb) {
