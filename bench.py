@@ -240,6 +240,49 @@ def run_ours(args):
         slot_n = (Ct.c_uint64 * 8)()
         L.p3d_profile_read(slot_ms, slot_n, 8, 1)
         L.p3d_profile_enable(0)
+        # ---- the other operating points SURVEY 8(d) asks for, same inputs, 10 device-timed steps each (N=1 only; context for
+        #      the headline, not part of it): training-time 48+48 sampling, bf16-stored planes, the single-pass bf16 decoder
+        #      and the fp32 SIMT parity kernels
+        variants = None
+        if world == 1 and not args.no_variants:
+            variants = {}
+            for name, ov, mm, pb in (('48+48 samples', dict(depth_resolution=48, depth_resolution_importance=48), mlp_mode, renderer.planes_bf16),
+                                     ('bf16-stored planes', {}, mlp_mode, True), ('tc_bf16 decoder (1 pass)', {}, 2, renderer.planes_bf16),
+                                     ('fp32_simt kernels', {}, 0, renderer.planes_bf16)):
+                rv = ImportanceRenderer(use_triplane=True)
+                rv.mlp_mode, rv.planes_bf16 = mm, pb
+                vo = dict(opts, **ov)
+
+                def vstep():
+                    c2w, K = labels_dev[:, :16].view(-1, 4, 4), labels_dev[:, 16:25].view(-1, 3, 3)
+                    ro, rd = sampler(c2w, K, R)
+                    rv._planes.key = None
+                    return rv(planes, decoder, ro, rd, vo)
+                for _ in range(3):
+                    vstep()
+                v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                v0.record()
+                for _ in range(10):
+                    vstep()
+                v1.record()
+                torch.cuda.synchronize()
+                variants[name] = {'value': round(VIEWS * 10 / (v0.elapsed_time(v1) * 1e-3), 1), 'unit': UNIT, 'steps': 10}
+                del rv
+        if variants is not None:
+            # the 256^3 sigma/rgb grid of get_eg3d_volume for one subject, one launch (reference: 168 chunks)
+            from panic3d_b200 import volume as pvol
+            for _ in range(2):
+                pvol.query_volume(planes[:1], decoder, opts, resolution=256, triplane_crop=0.1, cull_clouds=0.5, renderer=renderer)
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            v0.record()
+            for _ in range(3):
+                pvol.query_volume(planes[:1], decoder, opts, resolution=256, triplane_crop=0.1, cull_clouds=0.5, renderer=renderer)
+            v1.record()
+            torch.cuda.synchronize()
+            variants['volume query 256^3 (sigma+rgb+density+coords)'] = {'value': round(v0.elapsed_time(v1) / 3, 3), 'unit': 'ms/subject', 'steps': 3}
+            torch.cuda.empty_cache()
         # ---- e2e through the host-buffer C-ABI entry point (pinned host planes in, images out)
         e2e = None
         if not args.no_e2e:
@@ -287,6 +330,8 @@ def run_ours(args):
             out['e2e'] = {'value': world * VIEWS * e2e['steps'] / (e2e['ms'] * 1e-3), 'unit': UNIT,
                           'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'], 'steps': e2e['steps'],
                           'api': 'p3d_render_forward_host (C-ABI, pinned host buffers)'}
+        if variants:
+            out['variants'] = variants
         if world == 1 and not args.no_cpu_baseline:
             times, cores = cpu_reference_time(steps=3, warmup=1, views=1)
             out['cpu_baseline'] = {'value': len(times) / sum(times), 'unit': UNIT, 'cores': cores, 'kind': 'port',
@@ -345,6 +390,7 @@ def main():
     ap.add_argument('--planes', default=os.environ.get('P3D_BENCH_PLANES', 'fp32'), choices=['fp32', 'bf16'],
                     help='storage type of the channels-last tri-plane copy the gather reads (bf16 = fast mode, not parity)')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-variants', action='store_true', help='skip the 48+48 / bf16 / fp32_simt context measurements')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':

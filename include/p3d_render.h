@@ -160,6 +160,23 @@ int p3d_decode_points(const p3d_render_params* p, const void* planes,
                       const float* coords, int64_t n_points_per_view,
                       float* out_rgb, float* out_sigma, void* stream);
 
+/* Dense sigma / colour grid for mesh extraction: the renderer-level part of get_eg3d_volume
+   (_util/eg3d_metrics3d.py:94-183), which the reference evaluates as 168 host-side chunks of 100k points through
+   G.sample_mixed -> ImportanceRenderer.run_model with a .cpu() round trip per chunk.  One launch here:
+     * point n of view v (0 <= n < resolution^3) is the reference's create_samples point (eg3d_metrics3d.py:70-92),
+       reproduced bit for bit INCLUDING its un-floored float y/x indices, for cube_length = box_warp;
+     * results are written where the reference's reshape(R,R,R,.).flip(dims=(1,)) puts them: element (a,b,c) of view v
+       is point n = ((R-1-a)*R + b)*R + c.  out_sigma (N,R,R,R); out_rgb (N,R,R,R,out_dim-1) or NULL;
+       out_coords (N,R,R,R,3) or NULL; out_density (N,R,R,R) or NULL = sigma2density(sigma) with -1e3 where
+       triplane_crop (>= 0; negative = None) crops the point or where cull_clouds (>= 0; negative = None) culls it -
+       the cull test is applied to the density exactly as the reference does (cull_clouds_mask on densities,
+       eg3d_metrics3d.py:160-162).
+   Uses n_views, the plane / decoder fields and box_warp of *p; ray fields are ignored. */
+int p3d_volume_query(const p3d_render_params* p, const void* planes,
+                     const float* w1, const float* b1, const float* w2, const float* b2,
+                     int32_t resolution, double cube_length, double triplane_crop, double cull_clouds,
+                     float* out_sigma, float* out_rgb, float* out_density, float* out_coords, void* stream);
+
 /* End-to-end entry point with HOST buffers (what a non-torch caller binds): copies the
    NCHW fp32 tri-planes, decoder and cameras to the device, generates pinhole rays, renders and
    copies (rgb, depth, wsum, xyz) back.  Device buffers are cached between calls in a

@@ -399,6 +399,20 @@ int p3d_decode_points(const p3d_render_params* p, const void* planes, const floa
     return decode_points_v1(g, p, planes, w1, b1, w2, b2, coords, n_points_per_view, out_rgb, out_sigma, (cudaStream_t)stream);
 }
 
+int p3d_volume_query(const p3d_render_params* p, const void* planes, const float* w1, const float* b1, const float* w2,
+                     const float* b2, int32_t resolution, double cube_length, double triplane_crop, double cull_clouds,
+                     float* out_sigma, float* out_rgb, float* out_density, float* out_coords, void* stream) {
+    Geom g;
+    int rc = make_geom(p, &g);
+    if (rc) return rc;
+    P3D_REQUIRE(resolution >= 2 && resolution <= 1024, "resolution must be in [2, 1024], got %d", resolution);
+    P3D_REQUIRE(cube_length > 0, "cube_length must be > 0");
+    if (g.N == 0) return P3D_OK;
+    P3D_REQUIRE(planes && w1 && b1 && w2 && b2 && out_sigma, "null pointer");
+    return volume_query_v1(g, p, planes, w1, b1, w2, b2, resolution, cube_length, triplane_crop, cull_clouds, out_sigma,
+                           out_rgb, out_density, out_coords, (cudaStream_t)stream);
+}
+
 int p3d_render_forward_host(const p3d_render_params* p_in, const float* planes_nchw, const float* w1, const float* b1,
                             const float* w2, const float* b2, const float* cam2world, const float* intrinsics,
                             int32_t resolution, const float* u_coarse, const float* u_fine, float* out_rgb,

@@ -38,9 +38,37 @@ struct SampleArgs {
     long long total;            // samples in this launch
     long long per_view;         // samples per view (M*S, M*Sf or K)
     int per_ray;                // S, Sf (or 1 in points mode)
+    // volume mode (dense grid query, _util/eg3d_metrics3d.py:70-183)
+    int vol_res;                // grid side R: per_view = R^3
+    float vol_size, vol_origin; // voxel size cube/(R-1) and corner -cube/2, both rounded to fp32 like torch's scalar ops
+    float vol_crop, vol_cull;   // crop limit bw/2 - triplane_crop / cull threshold
+    bool vol_crop_on, vol_cull_on;
+    float* density_out;         // (total) or nullptr
+    float* coords_out;          // (total,3) or nullptr
 };
 
-enum { MODE_COARSE = 0, MODE_FINE = 1, MODE_POINTS = 2 };
+enum { MODE_COARSE = 0, MODE_FINE = 1, MODE_POINTS = 2, MODE_VOLUME = 3 };
+
+// Grid point n of the reference's create_samples (eg3d_metrics3d.py:70-92), bit for bit: the z index is the integer
+// n % R, but the y and x "indices" come from FLOAT divisions that are never floored - (float(n)/R) % R and
+// ((float(n)/R)/R) % R - so the lattice is sheared by a fraction of a voxel.  Meshes downstream were extracted from
+// exactly these points, so the shear is part of the contract.
+__device__ __forceinline__ void volume_point(long long n, int R, float vsize, float vorigin, float& x, float& y, float& z) {
+    const float nf = (float)n, Rf = (float)R;
+    const float iz = (float)(n % R);
+    const float q1 = __fdiv_rn(nf, Rf);
+    const float iy = fmodf(q1, Rf);
+    const float ix = fmodf(__fdiv_rn(q1, Rf), Rf);
+    x = __fadd_rn(__fmul_rn(ix, vsize), vorigin);
+    y = __fadd_rn(__fmul_rn(iy, vsize), vorigin);
+    z = __fadd_rn(__fmul_rn(iz, vsize), vorigin);
+}
+// where sample n of a view lands in the returned volume: reshape (R,R,R) by flat index, first axis flipped
+__device__ __forceinline__ long long volume_dest(long long n, int R) {
+    const long long rr = (long long)R * R;
+    const long long a = n / rr, rest = n - a * rr;
+    return ((long long)(R - 1) - a) * rr + rest;
+}
 
 
 
@@ -81,6 +109,8 @@ __global__ void __launch_bounds__(kTile) k_sample_decode(const SampleArgs a) {
             float py;
             if (MODE == MODE_POINTS) {
                 px = a.coords[gidx * 3 + 0]; py = a.coords[gidx * 3 + 1]; pz = a.coords[gidx * 3 + 2];
+            } else if (MODE == MODE_VOLUME) {
+                volume_point(gidx - (long long)view * a.per_view, a.vol_res, a.vol_size, a.vol_origin, px, py, pz);
             } else {
                 const long long ray = gidx / a.per_ray;
                 const int s = (int)(gidx - ray * a.per_ray);
@@ -146,8 +176,30 @@ __global__ void __launch_bounds__(kTile) k_sample_decode(const SampleArgs a) {
     }
     const long long gidx = tile0 + tid;
     float sigma = o[0];
-    if (MODE != MODE_POINTS) sigma = apply_masks(g, sigma, s_xz[tid * 2], s_xz[tid * 2 + 1]);
-    if (gidx < a.total) a.sigma_out[gidx] = sigma;
+    if (MODE == MODE_COARSE || MODE == MODE_FINE) sigma = apply_masks(g, sigma, s_xz[tid * 2], s_xz[tid * 2 + 1]);
+    if (MODE == MODE_VOLUME) {
+        if (gidx < a.total) {
+            const int view = (int)(gidx / a.per_view);
+            const long long n = gidx - (long long)view * a.per_view;
+            const long long dest = (long long)view * a.per_view + volume_dest(n, a.vol_res);
+            a.sigma_out[dest] = sigma;
+            if (a.density_out) {
+                // densities = sigma2density(sigma) (eg3d_metrics3d.py:65-69), then crop / cull write -1e3 (:155-162).  The
+                // reference hands the DENSITIES to cull_clouds_mask, which applies softplus(. - 1) -> 1 - exp(-.) once more
+                // (renderer.py:150-153): the threshold acts on the twice-transformed value.
+                float dens = 1.f - expf(-softplus_t(__fsub_rn(sigma, 1.f)));
+                const float px = s_xz[tid * 2], pz = s_xz[tid * 2 + 1];
+                if (a.vol_crop_on && !((fabsf(px) <= a.vol_crop) && (fabsf(pz) <= a.vol_crop))) dens = -1e3f;
+                if (a.vol_cull_on && (1.f - expf(-softplus_t(__fsub_rn(dens, 1.f)))) < a.vol_cull) dens = -1e3f;
+                a.density_out[dest] = dens;
+            }
+            if (a.coords_out) {
+                float x, y, z;
+                volume_point(n, a.vol_res, a.vol_size, a.vol_origin, x, y, z);
+                a.coords_out[dest * 3 + 0] = x; a.coords_out[dest * 3 + 1] = y; a.coords_out[dest * 3 + 2] = z;
+            }
+        }
+    } else if (gidx < a.total) a.sigma_out[gidx] = sigma;
     __syncthreads();                       // everyone has consumed its feature row
 #pragma unroll
     for (int c = 0; c < kRgb; ++c) {
@@ -157,10 +209,16 @@ __global__ void __launch_bounds__(kTile) k_sample_decode(const SampleArgs a) {
     }
     __syncthreads();
     // coalesced colour store: 128 rows x 32 floats
+    if (MODE == MODE_VOLUME && a.rgb_out == nullptr) return;
     for (int i = tid; i < kTile * kRgb; i += kTile) {
         const int row = i >> 5, col = i & 31;
-        const long long gi = tile0 + row;
-        if (gi < a.total) a.rgb_out[gi * kRgb + col] = s_feat[row * kFeatStride + col];
+        long long gi = tile0 + row;
+        if (gi >= a.total) continue;
+        if (MODE == MODE_VOLUME) {
+            const long long view = gi / a.per_view, n = gi - view * a.per_view;
+            gi = view * a.per_view + volume_dest(n, a.vol_res);
+        }
+        a.rgb_out[gi * kRgb + col] = s_feat[row * kFeatStride + col];
     }
 }
 
@@ -407,6 +465,22 @@ int decode_points_v1(const Geom& g, const p3d_render_params* p, const void* plan
     sa.sigma_out = out_sigma; sa.rgb_out = out_rgb;
     sa.total = (long long)g.N * n_pts; sa.per_view = n_pts; sa.per_ray = 1;
     return launch_sample_decode<MODE_POINTS>(sa, p->planes_bf16 != 0, stream);
+}
+
+int volume_query_v1(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
+                    const float* w2, const float* b2, int res, double cube_length, double triplane_crop, double cull_clouds,
+                    float* out_sigma, float* out_rgb, float* out_density, float* out_coords, cudaStream_t stream) {
+    SampleArgs sa{};
+    sa.g = g; sa.planes = planes; sa.w1 = w1; sa.b1 = b1; sa.w2 = w2; sa.b2 = b2;
+    sa.sigma_out = out_sigma; sa.rgb_out = out_rgb; sa.density_out = out_density; sa.coords_out = out_coords;
+    sa.per_view = (long long)res * res * res; sa.total = (long long)g.N * sa.per_view; sa.per_ray = 1;
+    sa.vol_res = res;
+    sa.vol_size = (float)(cube_length / (double)(res - 1));          // python float -> fp32 scalar operand
+    sa.vol_origin = (float)(0.0 - cube_length / 2.0);
+    sa.vol_crop = triplane_crop >= 0 ? (float)(p->box_warp / 2.0 - triplane_crop) : -1.f;    // renderer.py:139-148 (a limit < 0 crops everything, as there)
+    sa.vol_cull = cull_clouds >= 0 ? (float)cull_clouds : -1.f;
+    sa.vol_crop_on = triplane_crop >= 0; sa.vol_cull_on = cull_clouds >= 0;
+    return launch_sample_decode<MODE_VOLUME>(sa, p->planes_bf16 != 0, stream);
 }
 
 }  // namespace p3d

@@ -60,6 +60,15 @@ POINT_CASES = {
                            opts=_opts(depth_resolution=2, depth_resolution_importance=0), cameras=None),
 }
 
+# dense volume query (get_eg3d_volume, _util/eg3d_metrics3d.py:94-183): odd sides exercise the un-floored float indices
+VOLUME_CASES = {
+    'vol_plain13': dict(seed=41, N=1, P=64, R=1, res=13, opts=_opts(depth_resolution=2, depth_resolution_importance=0), cameras=None),
+    'vol_crop_cull16': dict(seed=42, N=1, P=64, R=1, res=16, triplane_crop=0.1, cull_clouds=0.35, sigma_bias=1.5,
+                            opts=_opts(depth_resolution=2, depth_resolution_importance=0), cameras=None),
+    'vol_crop0_eg3dplanes10': dict(seed=43, N=1, P=32, R=1, res=10, triplane_crop=0.0, use_triplane=False, force_sigmoid=True,
+                                   opts=_opts(depth_resolution=2, depth_resolution_importance=0), cameras=None),
+}
+
 
 def build_case_inputs(case):
     o = case['opts']

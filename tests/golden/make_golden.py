@@ -36,7 +36,7 @@ from training.volumetric_rendering.ray_sampler import RaySampler             # n
 import _databacks.lustrous_renders_v1 as ref_dk                              # noqa: E402
 
 from oracle import renderer_oracle as orc                                    # noqa: E402
-from tests.golden.cases import RENDER_CASES, POINT_CASES, build_case_inputs  # noqa: E402
+from tests.golden.cases import RENDER_CASES, POINT_CASES, VOLUME_CASES, build_case_inputs  # noqa: E402
 
 
 class _InjectRand:
@@ -123,6 +123,59 @@ def run_point_case(name, case):
     print(f'points_{name}: rgb mean {out["rgb"].mean():+.5f} sigma mean {out["sigma"].mean():+.5f}')
 
 
+def _reference_volume_functions():
+    """sigma2density / create_samples / get_eg3d_volume exactly as written in the reference, without importing the module
+    (its top-level imports need pyvista, dnnlib, legacy, ...): the three function definitions are sliced out of
+    _util/eg3d_metrics3d.py by their AST line ranges and executed in a namespace holding what they reference."""
+    import ast
+    from training.volumetric_rendering.renderer import triplane_crop_mask, cull_clouds_mask
+    path = REF + '/_util/eg3d_metrics3d.py'
+    src = open(path).read()
+    lines = src.splitlines(keepends=True)
+    want = {'sigma2density', 'create_samples', 'get_eg3d_volume'}
+    chunks = [''.join(lines[n.lineno - 1:n.end_lineno]) for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name in want]
+    assert len(chunks) == 3
+
+    class Dict(dict):
+        __getattr__ = dict.__getitem__
+        __setattr__ = dict.__setitem__
+    ns = dict(torch=torch, np=np, nn=torch.nn, Dict=Dict, device=torch.device('cpu'), triplane_crop_mask=triplane_crop_mask,
+              cull_clouds_mask=cull_clouds_mask)
+    exec(compile(''.join(chunks), path, 'exec'), ns)
+    return ns
+
+
+def run_volume_case(name, case):
+    """get_eg3d_volume (eg3d_metrics3d.py:94-183) on a stand-in G: f() resolves ws, sample_mixed() is the reference
+    ImportanceRenderer.run_model on fixed tri-planes (what TriPlaneGenerator.sample_mixed does after its backbone,
+    triplane.py:283-298)."""
+    ns = _reference_volume_functions()
+    planes, dec, _, _, _, _, opts = build_case_inputs(case)
+    renderer = ImportanceRenderer(use_triplane=case.get('use_triplane', True))
+    decoder = make_ref_decoder(dec)
+
+    class G:
+        rendering_kwargs = opts
+
+        @staticmethod
+        def f(xin):
+            xin['ws'] = torch.zeros(1, 14, 512)
+
+        @staticmethod
+        def sample_mixed(coords, dirs, ws, cond, **kw):
+            return renderer.run_model(planes.contiguous(), decoder, coords, dirs, opts)
+    xin = {'cond': None}
+    if 'triplane_crop' in case:
+        xin['triplane_crop'] = case['triplane_crop']
+    if 'cull_clouds' in case:
+        xin['cull_clouds'] = case['cull_clouds']
+    vol = ns['get_eg3d_volume'](G, xin, resolution=case['res'], max_batch=777)
+    np.savez_compressed(os.path.join(HERE, f'volume_{name}.npz'), coordinates=vol['coordinates'].numpy(), sigmas=vol['sigmas'].numpy(),
+                        rgbs=vol['rgbs'].numpy(), densities=vol['densities'].numpy(), case=json.dumps(case))
+    d = vol['densities']
+    print(f'volume_{name}: sigmas {tuple(vol["sigmas"].shape)} mean {vol["sigmas"].mean():+.4f} masked {(d == -1e3).float().mean():.3f}')
+
+
 def run_camera_table():
     """camera_params_to_matrix + get_rays_ortho + cam60/spin12 table (lustrous_renders_v1.py:14-104)."""
     cams = [(0.0, a, 1.0, 30.0) for a in range(-180, 180, 30)] + [(10.0, 30.0, 1.0, 30.0), (60.0, -45.0, 1.2, 45.0), (-20.0, 100.0, 0.9, 12.0)]
@@ -151,5 +204,8 @@ if __name__ == '__main__':
     for name, case in POINT_CASES.items():
         if not only or name in only:
             run_point_case(name, case)
+    for name, case in VOLUME_CASES.items():
+        if not only or name in only:
+            run_volume_case(name, case)
     if not only or 'cameras' in only:
         run_camera_table()
