@@ -283,6 +283,31 @@ def run_ours(args):
             torch.cuda.synchronize()
             variants['volume query 256^3 (sigma+rgb+density+coords)'] = {'value': round(v0.elapsed_time(v1) / 3, 3), 'unit': 'ms/subject', 'steps': 3}
             torch.cuda.empty_cache()
+            # training-path context (BASELINE configs[4] shape: batch_gpu 4, R=64, 48+48, 256^2 planes): forward + backward
+            # through the autograd Function (p3d_render_forward / p3d_render_backward), gradients to planes and decoder
+            with torch.enable_grad():
+                tp = torch.randn(4, 3, C, 256, 256, device=dev, requires_grad=True)
+                tdec = OSGDecoder(C, {'decoder_lr_mul': 1, 'decoder_output_dim': 32}).to(dev)
+                tro, trd = sampler(labels_dev[:4, :16].view(-1, 4, 4), labels_dev[:4, 16:25].view(-1, 3, 3), 64)
+                topts = dict(opts, depth_resolution=48, depth_resolution_importance=48)
+                rt = ImportanceRenderer(use_triplane=True)
+
+                def tstep():
+                    rgb, depth, wsum, _ = rt(tp, tdec, tro, trd, topts)
+                    (rgb.mean() + 0.1 * depth.mean() + 0.1 * wsum.mean()).backward()
+                    tp.grad = None
+                for _ in range(3):
+                    tstep()
+                v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                v0.record()
+                for _ in range(10):
+                    tstep()
+                v1.record()
+                torch.cuda.synchronize()
+                variants['training fwd+bwd (4 views, 64^2 rays, 48+48, 256^2 planes)'] = {'value': round(v0.elapsed_time(v1) / 10, 3), 'unit': 'ms/step', 'steps': 10}
+                del tp, tdec, rt
+            torch.cuda.empty_cache()
         # ---- e2e through the host-buffer C-ABI entry point (pinned host planes in, images out)
         e2e = None
         if not args.no_e2e:
