@@ -305,18 +305,61 @@ __global__ void __launch_bounds__(kT) k_sample_backward(const SampleBwdArgs a) {
         for (int k = 0; k < kC; ++k) s_dx[tid * kXs + k] = dx[k] * (1.f / 3.f);            // d(mean over 3 planes)
     }
     __syncthreads();
-    // ---- E) parameter gradients: reduce over the CTA's 128 samples, one red.global per element
-    for (int e = tid; e < kOut * kHidden; e += kT) {                 // dW2[m][j] = sum_s dlog[s][m] * hs[s][j]
-        const int m = e / kHidden, j = e - m * kHidden;
-        float acc = 0.f;
-        for (int sidx = 0; sidx < kT; ++sidx) acc = fmaf(s_do[sidx * kDs + m], s_hs[sidx * kHs + j], acc);
-        atomicAdd(a.d_w2 + e, acc * g.w2_gain);
-    }
-    for (int e = tid; e < kHidden * kC; e += kT) {                   // dW1[j][k] = sum_s dpre[s][j] * x[s][k]
-        const int j = e / kC, k = e - j * kC;
-        float acc = 0.f;
-        for (int sidx = 0; sidx < kT; ++sidx) acc = fmaf(s_dp[sidx * kHs + j], s_x[sidx * kXs + k], acc);
-        atomicAdd(a.d_w1 + e, acc * g.w1_gain);
+    // ---- E) parameter gradients: two small GEMMs over the CTA's 128 samples, register-blocked 4x4 per thread (8 shared
+    //         loads feed 16 FMAs; the first version's 2 loads per FMA made this phase the whole kernel's bottleneck),
+    //         then one red.global per element
+    {
+        // dW2[m][j] = sum_s dlog[s][m] * hs[s][j]: 9 x 16 blocks of 4x4 (rows 33..35 of the last block are padding)
+        for (int blk = tid; blk < 9 * 16; blk += kT) {
+            const int mb = blk >> 4, jb = blk & 15;
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+            for (int sidx = 0; sidx < kT; ++sidx) {
+                const float4 d4 = *reinterpret_cast<const float4*>(s_do + sidx * kDs + 4 * mb);
+                const float dl[4] = {d4.x, d4.y, d4.z, d4.w};
+                float hv[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) hv[j] = s_hs[sidx * kHs + 4 * jb + j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dl[i], hv[j], acc[i][j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = 4 * mb + i;
+                if (m >= kOut) continue;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(a.d_w2 + m * kHidden + 4 * jb + j, acc[i][j] * g.w2_gain);
+            }
+        }
+        // dW1[j][k] = sum_s dpre[s][j] * x[s][k]: 16 x 8 blocks of 4x4, one per thread
+        {
+            const int jb = tid >> 3, kb = tid & 7;
+            float acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+            for (int sidx = 0; sidx < kT; ++sidx) {
+                float dp[4], xv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { dp[i] = s_dp[sidx * kHs + 4 * jb + i]; xv[i] = s_x[sidx * kXs + 4 * kb + i]; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dp[i], xv[j], acc[i][j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) atomicAdd(a.d_w1 + (4 * jb + i) * kC + 4 * kb + j, acc[i][j] * g.w1_gain);
+        }
     }
     if (tid < kOut) {
         float acc = 0.f;
