@@ -66,3 +66,84 @@ def patch_generator(G):
     G.renderer = ImportanceRenderer(use_triplane=use_triplane)
     G.ray_sampler = RaySampler()
     return G
+
+
+class _PlaneMemo:
+    """Memo around ``G.backbone.synthesis``.  One subject's eval sweep calls ``G.f`` once per view - 16
+    camera views plus the warm-ups - and every call re-runs the 29 M-parameter StyleGAN2 backbone on the SAME
+    ``(ws, cond)`` (``triplane.py:188-196`` has ``use_cached_backbone`` / ``_last_planes`` for this, but ``G.f`` never sets
+    them, and ``get_eg3d_volume`` re-runs it 168 more times, ``_util/eg3d_metrics3d.py:125-151``).  The memo returns the
+    previous tri-planes when the latents and the conditioning are unchanged: compared by identity first, then by value
+    (``ws`` is (N,14,512): one tiny device compare per call).  Strong references to the key tensors are held so that a
+    freed-and-reallocated buffer can never alias a stale entry.  Training is untouched: calls under autograd
+    (``torch.is_grad_enabled()`` with any input requiring grad), with ``update_emas=True`` or with non-'const' noise
+    bypass the memo."""
+
+    def __init__(self, synthesis):
+        self.synthesis = synthesis
+        self.key = None
+        self.planes = None
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def _tensors(obj, out):
+        import torch
+        if isinstance(obj, torch.Tensor):
+            out.append(obj)
+        elif isinstance(obj, dict):
+            for k in sorted(obj, key=str):
+                _PlaneMemo._tensors(obj[k], out)
+        elif isinstance(obj, (list, tuple)):
+            for v in obj:
+                _PlaneMemo._tensors(v, out)
+        return out
+
+    @staticmethod
+    def _same(now, stored):
+        """stored: (tensor or clone, version at store time or None for a clone)."""
+        import torch
+        if len(now) != len(stored):
+            return False
+        for x, (y, ver) in zip(now, stored):
+            if ver is not None:
+                if y._version != ver:
+                    return False                                                  # the kept tensor was written in place: stale
+                if x is y:
+                    continue                                                      # same big tensor, untouched since
+            if x.shape != y.shape or x.dtype != y.dtype or x.device != y.device or not torch.equal(x, y):
+                return False
+        return True
+
+    def __call__(self, ws, cond=None, *args, **kwargs):
+        import torch
+        tensors = self._tensors([ws, cond, list(args), kwargs], [])
+        cacheable = (not kwargs.get('update_emas', False) and kwargs.get('noise_mode', 'const') == 'const'
+                     and not kwargs.get('return_more', False)
+                     and not (torch.is_grad_enabled() and any(t.requires_grad for t in tensors)))
+        scalars = repr(sorted((k, v) for k, v in kwargs.items() if not isinstance(v, (torch.Tensor, dict, list, tuple))))
+        if cacheable and self.key is not None and self.key[1] == scalars and self._same(tensors, self.key[0]):
+            self.hits += 1
+            return self.planes
+        planes = self.synthesis(ws, cond, *args, **kwargs)
+        if cacheable:
+            # small tensors (latents) are cloned; big ones (conditioning images / feature maps) are kept by reference with
+            # their version counter - an in-place write bumps it and forces the value comparison
+            self.key = ([(t.detach().clone(), None) if t.numel() <= 1 << 16 else (t, t._version) for t in tensors], scalars)
+            self.planes = planes
+            self.misses += 1
+        return planes
+
+    def clear(self):
+        self.key = self.planes = None
+
+
+def enable_plane_reuse(G):
+    """Wrap ``G.backbone.synthesis`` with a one-entry memo (see ``_PlaneMemo``); idempotent.  Returns the memo
+    (``.hits`` / ``.misses`` / ``.clear()``).  With it, a 16-view sweep of one subject through unchanged ``G.f`` runs the
+    backbone once, and the renderer's channels-last layout pass once (its plane cache keys on the same tensor)."""
+    syn = G.backbone.synthesis
+    if isinstance(syn, _PlaneMemo):
+        return syn
+    memo = _PlaneMemo(syn)
+    G.backbone.synthesis = memo
+    return memo
