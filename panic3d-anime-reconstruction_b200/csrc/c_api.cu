@@ -136,6 +136,50 @@ __global__ void k_planes_to_cl(const float* __restrict__ in, void* __restrict__ 
     }
 }
 
+// C == 32 fast path: a CTA moves a 32-channel x 128-pixel tile with 128-bit accesses on both sides.  Loads: a warp reads
+// 4 channels x 32 pixels (four 128-byte rows); the transposed tile tileT[pixel][channel] has pitch 33, which makes both
+// the scalar transposing stores (bank = 4q + j + c) and the channel-vector reads (bank = px + 4c4 + i) conflict-free;
+// stores: a warp writes 4 pixels x 32 channels = 512 contiguous bytes (256 for bf16).
+template <bool BF16>
+__global__ void __launch_bounds__(256) k_planes_to_cl32(const float* __restrict__ in, void* __restrict__ out, long long HW) {
+    __shared__ float tileT[128 * 33];
+    const long long plane = blockIdx.y;
+    const long long p0 = (long long)blockIdx.x * 128;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        const int c_sub = lane >> 3, q = lane & 7;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int task = warp + 8 * i, cg = task & 7, seg = task >> 3;
+            const long long px = p0 + 32 * seg + 4 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (px < HW) v = *reinterpret_cast<const float4*>(in + (plane * 32 + 4 * cg + c_sub) * HW + px);   // HW % 4 == 0
+            float* dst = tileT + (32 * seg + 4 * q) * 33 + 4 * cg + c_sub;
+            dst[0] = v.x; dst[33] = v.y; dst[66] = v.z; dst[99] = v.w;
+        }
+    }
+    __syncthreads();
+    {
+        const int c4 = lane & 7, px_sub = lane >> 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int pl = (warp + 8 * i) * 4 + px_sub;
+            const long long px = p0 + pl;
+            if (px >= HW) continue;
+            const float* src = tileT + pl * 33 + 4 * c4;
+            const float4 v = make_float4(src[0], src[1], src[2], src[3]);
+            const long long o = (plane * HW + px) * 32 + 4 * c4;
+            if (BF16) {
+                __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out) + o) =
+                    make_uint2(*reinterpret_cast<unsigned*>(&lo), *reinterpret_cast<unsigned*>(&hi));
+            } else {
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + o) = v;
+            }
+        }
+    }
+}
+
 // RaySampler.forward, ray_sampler.py:24-63
 __global__ void k_raygen_pinhole(const float* __restrict__ c2w, const float* __restrict__ K, int N, int R,
                                  float* __restrict__ ro, float* __restrict__ rd) {
@@ -259,6 +303,13 @@ int p3d_planes_to_channels_last(const float* planes_nchw, void* planes_cl, int64
     const long long HW = (long long)h * w;
     dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((channels + 31) / 32), (unsigned)n_planes), block(32, 8);
     ProfileScope prof(PROF_LAYOUT, (cudaStream_t)stream);
+    if (channels == 32 && HW % 4 == 0 && ((reinterpret_cast<uintptr_t>(planes_nchw) | reinterpret_cast<uintptr_t>(planes_cl)) & 15) == 0) {
+        dim3 g32((unsigned)((HW + 127) / 128), (unsigned)n_planes);
+        if (out_bf16) k_planes_to_cl32<true><<<g32, 256, 0, (cudaStream_t)stream>>>(planes_nchw, planes_cl, HW);
+        else k_planes_to_cl32<false><<<g32, 256, 0, (cudaStream_t)stream>>>(planes_nchw, planes_cl, HW);
+        P3D_LAUNCH_CHECK();
+        return P3D_OK;
+    }
     if (out_bf16) k_planes_to_cl<true><<<grid, block, 0, (cudaStream_t)stream>>>(planes_nchw, planes_cl, channels, HW);
     else k_planes_to_cl<false><<<grid, block, 0, (cudaStream_t)stream>>>(planes_nchw, planes_cl, channels, HW);
     P3D_LAUNCH_CHECK();

@@ -465,3 +465,18 @@ def test_fused_renderer_is_bit_reproducible():
     b, _ = gpu_render(RENDER_CASES['mid_eval96'], mlp_mode=1)
     for x, y in zip(a, b):
         assert torch.equal(x, y)
+
+
+@pytest.mark.parametrize('shape', [(5, 32, 20, 12), (3, 32, 64, 64), (2, 32, 7, 9), (6, 32, 128, 130)])
+@pytest.mark.parametrize('bf16', [False, True])
+def test_planes_to_channels_last_layout_pass(shape, bf16):
+    """p3d_planes_to_channels_last == permute(0,2,3,1) (+ bf16 rounding): vector fast path (HW % 4 == 0, incl. a partial
+    last 128-pixel tile) and the generic 32x32 transpose (odd HW)."""
+    from panic3d_b200 import _lib
+    dev = _dev()
+    n, c, h, w = shape
+    x = torch.randn(n, c, h, w, device=dev)
+    out = torch.empty((n, h, w, c), device=dev, dtype=torch.bfloat16 if bf16 else torch.float32)
+    _lib.check(_lib.lib().p3d_planes_to_channels_last(x.data_ptr(), out.data_ptr(), n, c, h, w, 1 if bf16 else 0, _lib.stream_ptr(dev)))
+    ref = x.permute(0, 2, 3, 1).contiguous()
+    assert torch.equal(out, ref.to(torch.bfloat16) if bf16 else ref)
