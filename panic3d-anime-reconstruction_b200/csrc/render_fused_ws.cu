@@ -54,7 +54,7 @@ struct __align__(1024) WsSmem {
     int2 taps[kGW][16][12];                       // 16 rows at a time per gather warp
     GroupState st[kStates];
     SlotState slot[2];
-    float rscratch[3072];                          // per-ray phases of the epilogue group (importance / merge)
+    float rscratch[3072];                          // per-ray phases: 2L floats per epilogue warp (importance / merge)
     unsigned long long a1_full[kNA], a1_empty[kNA], a2_full[2], a2_empty[2];
     unsigned long long d1_full, d1_empty, d2_full, dsig_empty;
     unsigned long long fine_ready[kStates], state_free[kStates];
@@ -402,184 +402,226 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             (tp.pass == 0 ? st.sg_c : st.sg_f)[srow] = sg;
         };
         auto ebar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };   // the eight epilogue warps
-        // ---- importance sampling for group n (renderer.py:328-387), 256 threads
-        auto importance = [&](int n) {
+        float* const scr = sm.rscratch + e * (2 * L);                    // this warp's private scratch (2L floats)
+        constexpr int NC = (S + 31) / 32, nb = S - 3;
+        constexpr int SC = (S > 64) ? 4 : 2;                               // 32-lane chunks of the padded uniform sort
+        // Per-ray phases, one warp per ray and no CTA-level barrier inside (at S=96 a group has 4 rays: epilogue warps 0-3
+        // take one each; at S=48 all eight warps do).  A warp on its own has nothing to hide latencies behind, so both
+        // phases are written for instruction-level
+        // parallelism: the 32-lane chunks of a ray are processed as independent chains (per-chunk scans, carries
+        // combined afterwards), every search is a fixed-trip branchless bisection, and the importance depths are put in
+        // order by sorting the UNIFORMS with a bitonic network (the inverse CDF is monotone, so mapping sorted uniforms
+        // yields sorted depths - this replaces the O(S^2) rank sort).
+        // ---- importance sampling of ray rl of group n (renderer.py:328-387)
+        auto importance_ray = [&](int n, int rl) {
             GroupState& st = sm.st[n & 3];
-            const int grp = (int)blockIdx.x + n * (int)gridDim.x;
-            const long long ray0 = (long long)grp * GR;
-            float* i_alpha = sm.rscratch;            // [384]
-            float* i_fac = sm.rscratch + 384;        // [384]
-            float* i_w = sm.rscratch + 768;          // [384]
-            float* i_cdf = sm.rscratch + 1152;       // [384]
-            float* i_tfu = sm.rscratch + 1536;       // [384]
-            constexpr int nb = S - 3;
-            ebar();                                   // sigma of the last coarse tile is in shared memory
-            for (int r = etid; r < kRowsG; r += 256) {
-                const int i = r % S;
+            const long long ray = (long long)((int)blockIdx.x + n * (int)gridDim.x) * GR + rl;
+            const float* tc = st.t_c + rl * S;
+            const float* sg = st.sg_c + rl * S;
+            float* i_w = scr;                     // [S]
+            float* i_cdf = scr + L / 2 + 32;      // [S] (S <= 96 -> fits the 2*L floats of this warp)
+            // uniforms first (global loads / Philox overlap the scans below); padded with +inf to 32*SC elements
+            float us[SC];
+#pragma unroll
+            for (int c = 0; c < SC; ++c) {
+                const int f = c * 32 + lane;
+                us[c] = INFINITY;
+                if (f < Sf && ray < a.R) us[c] = a.u_f ? a.u_f[ray * Sf + f] : philox_uniform(g.seed, (uint64_t)(ray * Sf + f), 1u);
+            }
+            float al[NC], inc[NC];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {        // alpha and (1 - alpha + 1e-10) per interval
+                const int i = c * 32 + lane;
                 float alpha = 0.f, fac = 1.f;
                 if (i < S - 1) {
-                    const float smid = __fsub_rn(__fmul_rn(__fadd_rn(st.sg_c[r], st.sg_c[r + 1]), 0.5f), 1.f);
-                    alpha = 1.f - ex2_approx(-kLog2e * __fmul_rn(softplus_mufu(smid), st.t_c[r + 1] - st.t_c[r]));
+                    const float smid = __fsub_rn(__fmul_rn(__fadd_rn(sg[i], sg[i + 1]), 0.5f), 1.f);
+                    alpha = 1.f - ex2_approx(-kLog2e * __fmul_rn(softplus_mufu(smid), tc[i + 1] - tc[i]));
                     fac = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
                 }
-                i_alpha[r] = alpha; i_fac[r] = fac;
+                al[c] = alpha; inc[c] = fac;
             }
-            ebar();
-            for (int rl = e; rl < GR; rl += kEW) {   // warp per ray: transmittance scan -> weights -> pooled pdf -> cdf
-                float carry = 1.f;
 #pragma unroll
-                for (int c = 0; c < (S + 31) / 32; ++c) {
-                    const int i = c * 32 + lane;
-                    const float f = i < S - 1 ? i_fac[rl * S + i] : 1.f;
-                    const float incl = warp_scan_mul(f, lane);
-                    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-                    if (lane == 0) excl = 1.f;
-                    if (i < S - 1) i_w[rl * S + i] = i_alpha[rl * S + i] * (carry * excl);
-                    carry *= __shfl_sync(0xffffffffu, incl, 31);
+            for (int c = 0; c < NC; ++c) inc[c] = warp_scan_mul(inc[c], lane);     // independent chains
+            float carry = 1.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int i = c * 32 + lane;
+                float excl = __shfl_up_sync(0xffffffffu, inc[c], 1);
+                if (lane == 0) excl = 1.f;
+                if (i < S) i_w[i] = al[c] * (carry * excl);
+                carry *= __shfl_sync(0xffffffffu, inc[c], 31);
+            }
+            __syncwarp();
+            float my[NC];
+            float part = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {        // max-pool(2) -> avg-pool(2) -> +0.01 -> +1e-5
+                const int k = c * 32 + lane;
+                float v = 0.f;
+                if (k < nb) {
+                    const float* w = i_w + k;
+                    v = __fadd_rn(__fadd_rn(__fmul_rn(__fadd_rn(fmaxf(w[0], w[1]), fmaxf(w[1], w[2])), 0.5f), 0.01f), 1e-5f);
                 }
-                __syncwarp();
-                float my[(S + 31) / 32];
-                float part = 0.f;
+                my[c] = v; part += v;
+            }
+            const float total = warp_sum(part);
 #pragma unroll
-                for (int c = 0; c < (S + 31) / 32; ++c) {
-                    const int k = c * 32 + lane;
-                    float v = 0.f;
-                    if (k < nb) {
-                        const float* w = i_w + rl * S + k;
-                        v = __fadd_rn(__fadd_rn(__fmul_rn(__fadd_rn(fmaxf(w[0], w[1]), fmaxf(w[1], w[2])), 0.5f), 0.01f), 1e-5f);
+            for (int c = 0; c < NC; ++c) my[c] = warp_scan_add((c * 32 + lane) < nb ? __fdiv_rn(my[c], total) : 0.f, lane);
+            float csum = 0.f;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const int k = c * 32 + lane;
+                const float incl = my[c] + csum;
+                if (k < nb) i_cdf[k + 1] = incl;
+                csum = __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (lane == 0) i_cdf[0] = 0.f;
+            // bitonic sort of the padded uniforms, element index c*32 + lane, ascending
+#pragma unroll
+            for (int k = 2; k <= 32 * SC; k <<= 1) {
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    if (j >= 32) {
+                        const int dc = j >> 5;
+#pragma unroll
+                        for (int c = 0; c < SC; ++c) {
+                            if ((c & dc) == 0) {
+                                const bool up = (((c * 32) & k) == 0);         // lane bits are below 32: direction depends on c only
+                                const float lo = fminf(us[c], us[c | dc]), hi = fmaxf(us[c], us[c | dc]);
+                                us[c] = up ? lo : hi; us[c | dc] = up ? hi : lo;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < SC; ++c) {
+                            const float other = __shfl_xor_sync(0xffffffffu, us[c], j);
+                            const bool up = (((c * 32 + lane) & k) == 0);
+                            const bool lower = (lane & j) == 0;
+                            us[c] = (lower == up) ? fminf(us[c], other) : fmaxf(us[c], other);
+                        }
                     }
-                    my[c] = v; part += v;
                 }
-                const float total = warp_sum(part);
-                float csum = 0.f;
-#pragma unroll
-                for (int c = 0; c < (S + 31) / 32; ++c) {
-                    const int k = c * 32 + lane;
-                    const float incl = warp_scan_add(k < nb ? __fdiv_rn(my[c], total) : 0.f, lane) + csum;
-                    if (k < nb) i_cdf[rl * S + k + 1] = incl;
-                    csum = __shfl_sync(0xffffffffu, incl, 31);
-                }
-                if (lane == 0) i_cdf[rl * S] = 0.f;
             }
-            ebar();
-            for (int r = etid; r < kRowsG; r += 256) {   // thread per importance sample: inverse CDF
-                const int rl = r / S, f = r - rl * S;
-                const long long ray = ray0 + rl;
+            __syncwarp();                         // i_cdf is complete
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {        // inverse CDF (searchsorted right=True), lerp between bin midpoints
+                const int f = c * 32 + lane;
+                if (f >= Sf) continue;
                 float val = INFINITY;
                 if (ray < a.R) {
-                    const float u = a.u_f ? a.u_f[ray * Sf + f] : philox_uniform(g.seed, (uint64_t)(ray * Sf + f), 1u);
-                    const float* cdf = i_cdf + rl * S;
-                    const float* t = st.t_c + rl * S;
-                    int lo = 0, hi = nb + 1;
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (cdf[mid] <= u) lo = mid + 1; else hi = mid; }
+                    const float u = us[c];
+                    int lo = 0;                   // number of cdf[0..nb] entries <= u
+#pragma unroll
+                    for (int step = 64; step >= 1; step >>= 1) {
+                        const int p = lo + step;
+                        const float x = i_cdf[min(p, nb + 1) - 1];
+                        if (p <= nb + 1 && x <= u) lo = p;
+                    }
                     const int below = max(lo - 1, 0), above = min(lo, nb);
-                    const float c0 = cdf[below], c1 = cdf[above];
-                    const float b0 = __fmul_rn(0.5f, __fadd_rn(t[below], t[below + 1]));
-                    const float b1 = __fmul_rn(0.5f, __fadd_rn(t[above], t[above + 1]));
+                    const float c0 = i_cdf[below], c1 = i_cdf[above];
+                    const float b0 = __fmul_rn(0.5f, __fadd_rn(tc[below], tc[below + 1]));
+                    const float b1 = __fmul_rn(0.5f, __fadd_rn(tc[above], tc[above + 1]));
                     float den = __fsub_rn(c1, c0);
                     if (den < 1e-5f) den = 1.f;
                     val = __fadd_rn(b0, __fmul_rn(__fdiv_rn(__fsub_rn(u, c0), den), __fsub_rn(b1, b0)));
                 }
-                i_tfu[r] = val;
+                st.t_f[rl * Sf + f] = val;
             }
-            ebar();
-            for (int r = etid; r < kRowsG; r += 256) {   // stable rank sort -> ascending importance depths
-                const int rl = r / S, j = r - rl * S;
-                const float tj = i_tfu[r];
-                const float4* row = reinterpret_cast<const float4*>(i_tfu + rl * S);
-                int rank = 0;
-#pragma unroll 4
-                for (int k4 = 0; k4 < S / 4; ++k4) {
-                    const float4 t4 = row[k4];
-                    const int k = 4 * k4;
-                    rank += (t4.x < tj || (t4.x == tj && k + 0 < j)) + (t4.y < tj || (t4.y == tj && k + 1 < j)) +
-                            (t4.z < tj || (t4.z == tj && k + 2 < j)) + (t4.w < tj || (t4.w == tj && k + 3 < j));
+            __syncwarp();
+        };
+        // ---- merge + transmittance + omega + per-ray outputs of ray rl of group n (renderer.py:289-301, ray_marcher.py:25-57)
+        auto composite_ray = [&](int n, int rl) {
+            GroupState& st = sm.st[n & 3];
+            SlotState& sl = sm.slot[n & 1];
+            const long long ray = (long long)((int)blockIdx.x + n * (int)gridDim.x) * GR + rl;
+            const float* tc = st.t_c + rl * S;
+            const float* tf = st.t_f + rl * Sf;
+            float* m_t = scr;                     // [L]
+            float* m_sg = scr + L;                // [L]
+            const bool rev = tc[0] > tc[S - 1];
+            const float* tca = rev ? tc + (S - 1) : tc;     // ascending view of the coarse depths: tca[m * dir]
+            const int dir = rev ? -1 : 1;
+            sl.acc[rl][lane] = 0.f;
+#pragma unroll
+            for (int c = 0; c < L / 32; ++c) {    // merge by rank: position = own index + count of the other list before it
+                const int r = c * 32 + lane;
+                const bool is_f = r >= S;
+                const int i = is_f ? r - S : r;
+                const int ci = rev ? S - 1 - i : i;
+                const float tv = is_f ? tf[i] : tc[ci];
+                int lo = 0;                       // coarse: #fine < tv; fine: #coarse <= tv  (stable: coarse first on ties)
+#pragma unroll
+                for (int step = 64; step >= 1; step >>= 1) {
+                    const int p = lo + step;
+                    const int q = min(p, S) - 1;                               // S == Sf
+                    const float x = is_f ? tca[q * dir] : tf[q];
+                    if (p <= S && (is_f ? (x <= tv) : (x < tv))) lo = p;
                 }
-                st.t_f[rl * Sf + rank] = tj;
+                const int pos = i + lo;
+                m_t[pos] = tv;
+                m_sg[pos] = is_f ? st.sg_f[rl * Sf + i] : st.sg_c[rl * S + ci];
+                sl.pos[is_f ? kRowsG + rl * Sf + i : rl * S + ci] = pos;
             }
+            __syncwarp();
+            float al[L / 32], inc[L / 32], tm[L / 32];
+#pragma unroll
+            for (int c = 0; c < L / 32; ++c) {
+                const int i = c * 32 + lane;
+                float alpha = 0.f, fac = 1.f, tmid = 0.f;
+                if (i < L - 1) {
+                    const float t0 = m_t[i], t1 = m_t[i + 1];
+                    const float smid = __fsub_rn(__fmul_rn(__fadd_rn(m_sg[i], m_sg[i + 1]), 0.5f), 1.f);
+                    alpha = 1.f - ex2_approx(-kLog2e * __fmul_rn(softplus_mufu(smid), t1 - t0));
+                    fac = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+                    tmid = __fmul_rn(__fadd_rn(t0, t1), 0.5f);
+                }
+                al[c] = alpha; inc[c] = fac; tm[c] = tmid;
+            }
+#pragma unroll
+            for (int c = 0; c < L / 32; ++c) inc[c] = warp_scan_mul(inc[c], lane);   // independent chains
+            float carry = 1.f, acc_w = 0.f, acc_d = 0.f, wprev = 0.f;
+#pragma unroll
+            for (int c = 0; c < L / 32; ++c) {
+                const int i = c * 32 + lane;
+                float excl = __shfl_up_sync(0xffffffffu, inc[c], 1);
+                if (lane == 0) excl = 1.f;
+                const float wi = al[c] * (carry * excl);
+                carry *= __shfl_sync(0xffffffffu, inc[c], 31);
+                acc_w += wi;
+                acc_d = fmaf(wi, tm[c], acc_d);
+                float wl = __shfl_up_sync(0xffffffffu, wi, 1);
+                if (lane == 0) wl = wprev;
+                wprev = __shfl_sync(0xffffffffu, wi, 31);
+                sl.om[rl * L + i] = __fmul_rn(__fadd_rn(wl, wi), 0.5f);
+            }
+            const float wsum = warp_sum(acc_w), dnum = warp_sum(acc_d);
+            const float back = g.white_back ? __fsub_rn(1.f, wsum) : 0.f;
+            if (ray < a.R) {
+                if (lane < 3) {
+                    const float v = fmaf(a.ro[ray * 3 + lane], wsum, a.rd[ray * 3 + lane] * dnum);
+                    a.out_xyz[ray * 3 + lane] = __fsub_rn(__fmul_rn(__fadd_rn(v, back), 2.f), 1.f);
+                }
+                if (lane == 0) {
+                    a.out_depth[ray] = __fdiv_rn(dnum, wsum);
+                    a.out_wsum[ray] = wsum;
+                    atomicMin(&a.bounds[0], float_to_ordered(m_t[0]));
+                    atomicMax(&a.bounds[1], float_to_ordered(m_t[L - 1]));
+                }
+            }
+            if (lane == 0) sl.back[rl] = back;
+            __syncwarp();
+        };
+        // ---- importance sampling for group n: barrier, warp per ray, barrier
+        auto importance = [&](int n) {
+            ebar();                                   // sigma of the last coarse tile is in shared memory
+            for (int rl = e; rl < GR; rl += kEW) importance_ray(n, rl);
             ebar();
             if (etid == 0) mbar_arrive(&sm.fine_ready[n & 3]);
         };
-        // ---- merge + transmittance + omega for group n (renderer.py:289-301, ray_marcher.py:25-44), 256 threads
+        // ---- merge + transmittance + omega for group n: barrier, warp per ray, barrier
         auto composite = [&](int n) {
-            GroupState& st = sm.st[n & 3];
-            SlotState& sl = sm.slot[n & 1];
-            const int grp = (int)blockIdx.x + n * (int)gridDim.x;
-            const long long ray0 = (long long)grp * GR;
-            float* m_t = sm.rscratch;                // [GR][L] = 768
-            float* m_sg = sm.rscratch + 768;
-            float* m_al = sm.rscratch + 1536;
-            float* m_fc = sm.rscratch + 2304;
             ebar();
-            if (etid < GR * kRgb) sl.acc[etid >> 5][etid & 31] = 0.f;
-            for (int r = etid; r < 2 * kRowsG; r += 256) {
-                const bool is_f = r >= kRowsG;
-                const int row = is_f ? r - kRowsG : r;
-                const int rl = row / S, i = row - rl * S;
-                const float* tc = st.t_c + rl * S;
-                const float* tf = st.t_f + rl * Sf;
-                const bool rev = tc[0] > tc[S - 1];
-                if (!is_f) {
-                    const int ci = rev ? S - 1 - i : i;
-                    const float tv = tc[ci];
-                    int lo = 0, hi = Sf;
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tf[mid] < tv) lo = mid + 1; else hi = mid; }
-                    const int pos = i + lo;
-                    m_t[rl * L + pos] = tv; m_sg[rl * L + pos] = st.sg_c[rl * S + ci]; sl.pos[rl * S + ci] = pos;
-                } else {
-                    const float tv = tf[i];
-                    int lo = 0, hi = S;
-                    while (lo < hi) { const int mid = (lo + hi) >> 1; if (tc[rev ? S - 1 - mid : mid] <= tv) lo = mid + 1; else hi = mid; }
-                    const int pos = i + lo;
-                    m_t[rl * L + pos] = tv; m_sg[rl * L + pos] = st.sg_f[row]; sl.pos[kRowsG + row] = pos;
-                }
-            }
-            ebar();
-            for (int r = etid; r < 2 * kRowsG; r += 256) {
-                const int i = r % L;
-                float alpha = 0.f, fac = 1.f;
-                if (i < L - 1) {
-                    const float smid = __fsub_rn(__fmul_rn(__fadd_rn(m_sg[r], m_sg[r + 1]), 0.5f), 1.f);
-                    alpha = 1.f - ex2_approx(-kLog2e * __fmul_rn(softplus_mufu(smid), m_t[r + 1] - m_t[r]));
-                    fac = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
-                }
-                m_al[r] = alpha; m_fc[r] = fac;
-            }
-            ebar();
-            for (int rl = e; rl < GR; rl += kEW) {
-                const long long ray = ray0 + rl;
-                float carry = 1.f, acc_w = 0.f, acc_d = 0.f, wprev = 0.f;
-#pragma unroll
-                for (int c = 0; c < L / 32; ++c) {
-                    const int i = c * 32 + lane;
-                    const float incl = warp_scan_mul(m_fc[rl * L + i], lane);
-                    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-                    if (lane == 0) excl = 1.f;
-                    const float wi = m_al[rl * L + i] * (carry * excl);
-                    carry *= __shfl_sync(0xffffffffu, incl, 31);
-                    acc_w += wi;
-                    if (i < L - 1) acc_d = fmaf(wi, __fmul_rn(__fadd_rn(m_t[rl * L + i], m_t[rl * L + i + 1]), 0.5f), acc_d);
-                    float wl = __shfl_up_sync(0xffffffffu, wi, 1);
-                    if (lane == 0) wl = wprev;
-                    wprev = __shfl_sync(0xffffffffu, wi, 31);
-                    sl.om[rl * L + i] = __fmul_rn(__fadd_rn(wl, wi), 0.5f);
-                }
-                const float wsum = warp_sum(acc_w), dnum = warp_sum(acc_d);
-                const float back = g.white_back ? __fsub_rn(1.f, wsum) : 0.f;
-                if (ray < a.R) {
-                    if (lane < 3) {
-                        const float v = fmaf(a.ro[ray * 3 + lane], wsum, a.rd[ray * 3 + lane] * dnum);
-                        a.out_xyz[ray * 3 + lane] = __fsub_rn(__fmul_rn(__fadd_rn(v, back), 2.f), 1.f);
-                    }
-                    if (lane == 0) {
-                        a.out_depth[ray] = __fdiv_rn(dnum, wsum);
-                        a.out_wsum[ray] = wsum;
-                        atomicMin(&a.bounds[0], float_to_ordered(m_t[rl * L]));
-                        atomicMax(&a.bounds[1], float_to_ordered(m_t[rl * L + L - 1]));
-                    }
-                }
-                if (lane == 0) sl.back[rl] = back;
-            }
+            for (int rl = e; rl < GR; rl += kEW) composite_ray(n, rl);
             ebar();
         };
         auto colours = [&](int n) {                                        // sum_j omega_j * rgb_j for group n, from TMEM
