@@ -137,6 +137,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
     uint32_t r;
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r) : "r"(taddr) : "memory");
@@ -630,45 +641,98 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             tc_fence_after();
             const int grp = (int)blockIdx.x + n * (int)gridDim.x;
             const long long ray0 = (long long)grp * GR;
-            // A warp's 32 TMEM rows are the same ray(s) in each of its three tiles, so the per-tile column sums are
-            // first added up in a register and published once: every (ray, channel) cell of sl.acc then receives
-            // exactly two shared-memory adds (one per chunk), whose order cannot change the rounded sum - the kernel
-            // is bit-reproducible run to run and independent of how the rays are batched.
-            float part[2] = {0.f, 0.f};
-            const int rl_first = (quarter * 32) / RPT;
-            for (int i = 0; i < 3; ++i) {
-                const int tile6 = chunk + 2 * i;                           // this warp's tiles: {0,2,4} or {1,3,5}
-                const int pass = tile6 / 3, k = tile6 - pass * 3;
+            if (RPT == 32) {                                           // S = 96: one ray per warp (measured faster in this form)
+                // A warp's 32 TMEM rows are the same ray(s) in each of its three tiles, so the per-tile column sums are
+                // first added up in a register and published once: every (ray, channel) cell of sl.acc then receives
+                // exactly two shared-memory adds (one per chunk), whose order cannot change the rounded sum - the kernel
+                // is bit-reproducible run to run and independent of how the rays are batched.
+                float part[2] = {0.f, 0.f};
+                const int rl_first = (quarter * 32) / RPT;
+                for (int i = 0; i < 3; ++i) {
+                    const int tile6 = chunk + 2 * i;                           // this warp's tiles: {0,2,4} or {1,3,5}
+                    const int pass = tile6 / 3, k = tile6 - pass * 3;
+                    const int trow = quarter * 32 + lane;
+                    const int rl = trow / RPT, s = k * RPT + (trow - rl * RPT);
+                    const bool live = ray0 + rl < a.R;
+                    const float om = live ? sl.om[rl * L + sl.pos[pass * kRowsG + rl * S + s]] : 0.f;
+                    const float ca = g.force_sigmoid ? om : 1.002f * om, cb = g.force_sigmoid ? 0.f : -0.001f * om;
+                    float v[32];
+                    tmem_ld32(tmem + kColD2 + (slot_i * 6 + tile6) * 32 + lane_base, v);
+    #pragma unroll
+                    for (int c = 0; c < kRgb; ++c) v[c] = fmaf(rcp_approx(1.f + ex2_approx(v[c] + sm.b2c[c])), ca, cb);
+    #pragma unroll
+                    for (int t2 = 0; t2 < 32 / RPT; ++t2) {
+                        const int target = rl_first + t2;
+                        float r[32];
+    #pragma unroll
+                        for (int c = 0; c < 32; ++c) r[c] = (RPT == 32 || rl == target) ? v[c] : 0.f;
+    #pragma unroll
+                        for (int off = 16; off >= 1; off >>= 1) {
+                            const bool up = (lane & off) != 0;
+    #pragma unroll
+                            for (int j = 0; j < off; ++j) {
+                                const float send = up ? r[j] : r[j + off];
+                                const float keep = up ? r[j + off] : r[j];
+                                r[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                            }
+                        }
+                        part[t2] += r[0];
+                    }
+                }
+    #pragma unroll
+                for (int t2 = 0; t2 < 32 / RPT; ++t2) atomicAdd(&sl.acc[rl_first + t2][lane], part[t2]);
+            } else {                                                   // S = 48: two rays per warp
+                // A warp's 32 TMEM rows are the same ray(s) in each of its three tiles, so the omega-weighted colours of the
+                // three tiles are first summed per row in registers (16 columns at a time) and only then reduced over the
+                // rows with ONE transposing butterfly per half (16 shuffles instead of 31 per tile).  Every (ray, channel)
+                // cell of sl.acc receives exactly two shared-memory adds (one per chunk), whose order cannot change the
+                // rounded sum - the kernel is bit-reproducible run to run and independent of how the rays are batched.
+                const int rl_first = (quarter * 32) / RPT;
                 const int trow = quarter * 32 + lane;
-                const int rl = trow / RPT, s = k * RPT + (trow - rl * RPT);
+                const int rl = trow / RPT, s_in = trow - rl * RPT;
                 const bool live = ray0 + rl < a.R;
-                const float om = live ? sl.om[rl * L + sl.pos[pass * kRowsG + rl * S + s]] : 0.f;
-                const float ca = g.force_sigmoid ? om : 1.002f * om, cb = g.force_sigmoid ? 0.f : -0.001f * om;
-                float v[32];
-                tmem_ld32(tmem + kColD2 + (slot_i * 6 + tile6) * 32 + lane_base, v);
-#pragma unroll
-                for (int c = 0; c < kRgb; ++c) v[c] = fmaf(rcp_approx(1.f + ex2_approx(v[c] + sm.b2c[c])), ca, cb);
-#pragma unroll
-                for (int t2 = 0; t2 < 32 / RPT; ++t2) {
-                    const int target = rl_first + t2;
-                    float r[32];
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) r[c] = (RPT == 32 || rl == target) ? v[c] : 0.f;
-#pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) {
+                float ca[3], cb[3];
+    #pragma unroll
+                for (int i = 0; i < 3; ++i) {
+                    const int tile6 = chunk + 2 * i;                           // this warp's tiles: {0,2,4} or {1,3,5}
+                    const int pass = tile6 / 3, k = tile6 - pass * 3;
+                    const float om = live ? sl.om[rl * L + sl.pos[pass * kRowsG + rl * S + k * RPT + s_in]] : 0.f;
+                    ca[i] = g.force_sigmoid ? om : 1.002f * om; cb[i] = g.force_sigmoid ? 0.f : -0.001f * om;
+                }
+    #pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    float r[16];
+    #pragma unroll
+                    for (int c = 0; c < 16; ++c) r[c] = 0.f;
+    #pragma unroll
+                    for (int i = 0; i < 3; ++i) {
+                        const int tile6 = chunk + 2 * i;
+                        float v[16];
+                        tmem_ld16(tmem + kColD2 + (slot_i * 6 + tile6) * 32 + 16 * h + lane_base, v);
+    #pragma unroll
+                        for (int c = 0; c < 16; ++c) r[c] += fmaf(rcp_approx(1.f + ex2_approx(v[c] + sm.b2c[16 * h + c])), ca[i], cb[i]);
+                    }
+                    // rows -> one value per lane: RPT == 32 reduces all 32 lanes (column = lane >> 1 after the final pair add),
+                    // RPT == 16 reduces each 16-lane half separately (column = lane & 15, ray = rl_first + (lane >> 4))
+    #pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                        const int off = (RPT == 32 ? 16 : 8) >> st, n2 = 8 >> st;
                         const bool up = (lane & off) != 0;
-#pragma unroll
-                        for (int j = 0; j < off; ++j) {
-                            const float send = up ? r[j] : r[j + off];
-                            const float keep = up ? r[j + off] : r[j];
+    #pragma unroll
+                        for (int j = 0; j < n2; ++j) {
+                            const float send = up ? r[j] : r[j + n2];
+                            const float keep = up ? r[j + n2] : r[j];
                             r[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
                         }
                     }
-                    part[t2] += r[0];
+                    if (RPT == 32) {
+                        r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
+                        if ((lane & 1) == 0) atomicAdd(&sl.acc[rl_first][16 * h + (lane >> 1)], r[0]);
+                    } else {
+                        atomicAdd(&sl.acc[rl_first + (lane >> 4)][16 * h + (lane & 15)], r[0]);
+                    }
                 }
             }
-#pragma unroll
-            for (int t2 = 0; t2 < 32 / RPT; ++t2) atomicAdd(&sl.acc[rl_first + t2][lane], part[t2]);
             tc_fence_before();
             asm volatile("bar.sync 1, 256;" ::: "memory");                 // all eight epilogue warps
             if (etid < GR * kRgb) {
