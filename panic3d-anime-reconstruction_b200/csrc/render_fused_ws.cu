@@ -137,6 +137,31 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};\n\t"
+        "tcgen05.wait::st.sync.aligned;"
+        :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+           "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+           "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+           "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+           "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+           "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+           "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+           "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n\t"
+        "tcgen05.wait::st.sync.aligned;"
+        :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+           "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+           "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+           "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
     uint32_t r[16];
     asm volatile(
@@ -622,10 +647,29 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             if (lane == 0) sl.back[rl] = back;
             __syncwarp();
         };
+        // At S = 96 a group has four rays, so epilogue warps 4-7 have nothing to do in the per-ray phases: they use the
+        // time to turn the group's parked colour logits into colours IN PLACE in TMEM (sigmoid = rcp(1 + ex2(.)), the
+        // MUFU half of the colour reduction), coarse tiles during importance, fine tiles during merge.  colours(n) is
+        // then a load + FMA + reduction.  (At S = 48 all eight warps carry a ray and the logits stay raw.)
+        constexpr bool kPreSig = (GR <= kEW / 2);
+        auto sigmoid_in_place = [&](int n, int pass) {
+            tc_fence_after();
+#pragma unroll 1
+            for (int k = 0; k < 6; ++k) {                              // 3 tiles x 2 halves of 16 columns (keeps 16 registers live)
+                const uint32_t taddr = tmem + kColD2 + ((n & 1) * 6 + pass * 3 + (k >> 1)) * 32 + 16 * (k & 1) + lane_base;
+                float v[16];
+                tmem_ld16(taddr, v);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) v[c] = rcp_approx(1.f + ex2_approx(v[c] + sm.b2c[16 * (k & 1) + c]));
+                tmem_st16(taddr, v);
+            }
+            tc_fence_before();
+        };
         // ---- importance sampling for group n: barrier, warp per ray, barrier
         auto importance = [&](int n) {
             ebar();                                   // sigma of the last coarse tile is in shared memory
             for (int rl = e; rl < GR; rl += kEW) importance_ray(n, rl);
+            if (kPreSig && e >= kEW / 2) sigmoid_in_place(n, 0);
             ebar();
             if (etid == 0) mbar_arrive(&sm.fine_ready[n & 3]);
         };
@@ -633,6 +677,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
         auto composite = [&](int n) {
             ebar();
             for (int rl = e; rl < GR; rl += kEW) composite_ray(n, rl);
+            if (kPreSig && e >= kEW / 2) sigmoid_in_place(n, 1);
             ebar();
         };
         auto colours = [&](int n) {                                        // sum_j omega_j * rgb_j for group n, from TMEM
@@ -659,7 +704,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
                     float v[32];
                     tmem_ld32(tmem + kColD2 + (slot_i * 6 + tile6) * 32 + lane_base, v);
     #pragma unroll
-                    for (int c = 0; c < kRgb; ++c) v[c] = fmaf(rcp_approx(1.f + ex2_approx(v[c] + sm.b2c[c])), ca, cb);
+                    for (int c = 0; c < kRgb; ++c) v[c] = fmaf(kPreSig ? v[c] : rcp_approx(1.f + ex2_approx(v[c] + sm.b2c[c])), ca, cb);
     #pragma unroll
                     for (int t2 = 0; t2 < 32 / RPT; ++t2) {
                         const int target = rl_first + t2;
