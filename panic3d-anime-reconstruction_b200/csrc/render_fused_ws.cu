@@ -449,14 +449,11 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
         // order by sorting the UNIFORMS with a bitonic network (the inverse CDF is monotone, so mapping sorted uniforms
         // yields sorted depths - this replaces the O(S^2) rank sort).
         // ---- importance sampling of ray rl of group n (renderer.py:328-387)
-        auto importance_ray = [&](int n, int rl) {
-            GroupState& st = sm.st[n & 3];
+        // ---- sorted importance uniforms of ray rl -> dst[0..Sf): independent of the densities, so at S = 96 the ray's
+        //      partner warp (epilogue warps 4-7) does it while the ray's own warp builds the cdf
+        auto sort_uniforms = [&](int n, int rl, float* dst) {
             const long long ray = (long long)((int)blockIdx.x + n * (int)gridDim.x) * GR + rl;
-            const float* tc = st.t_c + rl * S;
-            const float* sg = st.sg_c + rl * S;
-            float* i_w = scr;                     // [S]
-            float* i_cdf = scr + L / 2 + 32;      // [S] (S <= 96 -> fits the 2*L floats of this warp)
-            // uniforms first (global loads / Philox overlap the scans below); padded with +inf to 32*SC elements
+            // padded with +inf to 32*SC elements
             float us[SC];
 #pragma unroll
             for (int c = 0; c < SC; ++c) {
@@ -464,6 +461,43 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
                 us[c] = INFINITY;
                 if (f < Sf && ray < a.R) us[c] = a.u_f ? a.u_f[ray * Sf + f] : philox_uniform(g.seed, (uint64_t)(ray * Sf + f), 1u);
             }
+            // bitonic sort of the padded uniforms, element index c*32 + lane, ascending
+#pragma unroll
+            for (int k = 2; k <= 32 * SC; k <<= 1) {
+#pragma unroll
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    if (j >= 32) {
+                        const int dc = j >> 5;
+#pragma unroll
+                        for (int c = 0; c < SC; ++c) {
+                            if ((c & dc) == 0) {
+                                const bool up = (((c * 32) & k) == 0);         // lane bits are below 32: direction depends on c only
+                                const float lo = fminf(us[c], us[c | dc]), hi = fmaxf(us[c], us[c | dc]);
+                                us[c] = up ? lo : hi; us[c | dc] = up ? hi : lo;
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < SC; ++c) {
+                            const float other = __shfl_xor_sync(0xffffffffu, us[c], j);
+                            const bool up = (((c * 32 + lane) & k) == 0);
+                            const bool lower = (lane & j) == 0;
+                            us[c] = (lower == up) ? fminf(us[c], other) : fmaxf(us[c], other);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NC; ++c)
+                if (c * 32 + lane < Sf) dst[c * 32 + lane] = us[c];
+        };
+        auto importance_ray = [&](int n, int rl, const float* sorted_u, int pair_bar) {
+            GroupState& st = sm.st[n & 3];
+            const long long ray = (long long)((int)blockIdx.x + n * (int)gridDim.x) * GR + rl;
+            const float* tc = st.t_c + rl * S;
+            const float* sg = st.sg_c + rl * S;
+            float* i_w = scr;                     // [S]
+            float* i_cdf = scr + L / 2 + 32;      // [S] (S <= 96 -> fits the 2*L floats of this warp)
             float al[NC], inc[NC];
 #pragma unroll
             for (int c = 0; c < NC; ++c) {        // alpha and (1 - alpha + 1e-10) per interval
@@ -512,40 +546,15 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
                 csum = __shfl_sync(0xffffffffu, incl, 31);
             }
             if (lane == 0) i_cdf[0] = 0.f;
-            // bitonic sort of the padded uniforms, element index c*32 + lane, ascending
-#pragma unroll
-            for (int k = 2; k <= 32 * SC; k <<= 1) {
-#pragma unroll
-                for (int j = k >> 1; j > 0; j >>= 1) {
-                    if (j >= 32) {
-                        const int dc = j >> 5;
-#pragma unroll
-                        for (int c = 0; c < SC; ++c) {
-                            if ((c & dc) == 0) {
-                                const bool up = (((c * 32) & k) == 0);         // lane bits are below 32: direction depends on c only
-                                const float lo = fminf(us[c], us[c | dc]), hi = fmaxf(us[c], us[c | dc]);
-                                us[c] = up ? lo : hi; us[c | dc] = up ? hi : lo;
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < SC; ++c) {
-                            const float other = __shfl_xor_sync(0xffffffffu, us[c], j);
-                            const bool up = (((c * 32 + lane) & k) == 0);
-                            const bool lower = (lane & j) == 0;
-                            us[c] = (lower == up) ? fminf(us[c], other) : fmaxf(us[c], other);
-                        }
-                    }
-                }
-            }
-            __syncwarp();                         // i_cdf is complete
+            if (pair_bar >= 0) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");   // partner's sorted uniforms + own i_cdf
+            else __syncwarp();                    // i_cdf is complete
 #pragma unroll
             for (int c = 0; c < NC; ++c) {        // inverse CDF (searchsorted right=True), lerp between bin midpoints
                 const int f = c * 32 + lane;
                 if (f >= Sf) continue;
                 float val = INFINITY;
                 if (ray < a.R) {
-                    const float u = us[c];
+                    const float u = sorted_u[f];
                     int lo = 0;                   // number of cdf[0..nb] entries <= u
 #pragma unroll
                     for (int step = 64; step >= 1; step >>= 1) {
@@ -668,8 +677,23 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
         // ---- importance sampling for group n: barrier, warp per ray, barrier
         auto importance = [&](int n) {
             ebar();                                   // sigma of the last coarse tile is in shared memory
-            for (int rl = e; rl < GR; rl += kEW) importance_ray(n, rl);
-            if (kPreSig && e >= kEW / 2) sigmoid_in_place(n, 0);
+            if (kPreSig) {                            // S = 96: warp e < 4 owns ray e, warp e + 4 is its helper (named barrier 2 + e)
+                if (e < kEW / 2) {
+                    if (e < GR) importance_ray(n, e, sm.rscratch + (e + kEW / 2) * (2 * L), 2 + e);
+                } else {
+                    if (e - kEW / 2 < GR) {
+                        sort_uniforms(n, e - kEW / 2, scr);
+                        asm volatile("bar.sync %0, 64;" ::"r"(2 + e - kEW / 2) : "memory");
+                    }
+                    sigmoid_in_place(n, 0);
+                }
+            } else {
+                for (int rl = e; rl < GR; rl += kEW) {
+                    sort_uniforms(n, rl, scr + L + L / 3);           // [128, 192) of this warp's 2L = 192 floats at S = 48
+                    __syncwarp();
+                    importance_ray(n, rl, scr + L + L / 3, -1);
+                }
+            }
             ebar();
             if (etid == 0) mbar_arrive(&sm.fine_ready[n & 3]);
         };
