@@ -575,20 +575,23 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             __syncwarp();
         };
         // ---- merge + transmittance + omega + per-ray outputs of ray rl of group n (renderer.py:289-301, ray_marcher.py:25-57)
-        auto composite_ray = [&](int n, int rl) {
+        // (mscr, chunks [c0, c1), pair_bar, finish): at S = 96 the ray's warp merges the coarse chunks and its partner the fine
+        // chunks into the same scratch; they meet at named barrier pair_bar and the ray's warp finishes alone
+        auto composite_ray = [&](int n, int rl, float* mscr, int c0, int c1, int pair_bar, bool finish) {
             GroupState& st = sm.st[n & 3];
             SlotState& sl = sm.slot[n & 1];
             const long long ray = (long long)((int)blockIdx.x + n * (int)gridDim.x) * GR + rl;
             const float* tc = st.t_c + rl * S;
             const float* tf = st.t_f + rl * Sf;
-            float* m_t = scr;                     // [L]
-            float* m_sg = scr + L;                // [L]
+            float* m_t = mscr;                    // [L]
+            float* m_sg = mscr + L;               // [L]
             const bool rev = tc[0] > tc[S - 1];
             const float* tca = rev ? tc + (S - 1) : tc;     // ascending view of the coarse depths: tca[m * dir]
             const int dir = rev ? -1 : 1;
-            sl.acc[rl][lane] = 0.f;
+            if (finish) sl.acc[rl][lane] = 0.f;
 #pragma unroll
             for (int c = 0; c < L / 32; ++c) {    // merge by rank: position = own index + count of the other list before it
+                if (c < c0 || c >= c1) continue;
                 const int r = c * 32 + lane;
                 const bool is_f = r >= S;
                 const int i = is_f ? r - S : r;
@@ -607,7 +610,9 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
                 m_sg[pos] = is_f ? st.sg_f[rl * Sf + i] : st.sg_c[rl * S + ci];
                 sl.pos[is_f ? kRowsG + rl * Sf + i : rl * S + ci] = pos;
             }
-            __syncwarp();
+            if (pair_bar >= 0) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+            else __syncwarp();
+            if (!finish) return;
             float al[L / 32], inc[L / 32], tm[L / 32];
 #pragma unroll
             for (int c = 0; c < L / 32; ++c) {
@@ -700,8 +705,17 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
         // ---- merge + transmittance + omega for group n: barrier, warp per ray, barrier
         auto composite = [&](int n) {
             ebar();
-            for (int rl = e; rl < GR; rl += kEW) composite_ray(n, rl);
-            if (kPreSig && e >= kEW / 2) sigmoid_in_place(n, 1);
+            if (kPreSig) {
+                if (e < kEW / 2) {
+                    if (e < GR) composite_ray(n, e, scr, 0, L / 64, 2 + e, true);
+                } else {
+                    const int rl = e - kEW / 2;
+                    if (rl < GR) composite_ray(n, rl, sm.rscratch + rl * (2 * L), L / 64, L / 32, 2 + rl, false);
+                    sigmoid_in_place(n, 1);
+                }
+            } else {
+                for (int rl = e; rl < GR; rl += kEW) composite_ray(n, rl, scr, 0, L / 32, -1, true);
+            }
             ebar();
         };
         auto colours = [&](int n) {                                        // sum_j omega_j * rgb_j for group n, from TMEM
