@@ -339,8 +339,8 @@ def run_ours(args):
         else:
             roof = {'bound': 'hbm', 'achieved': byts / (kern_ms * 1e-3) / 1e9, 'peak': hbm_gbs, 'unit': 'GB/s'}
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
-        # command (profiles/r1_final_ws_raw.csv: 631.5 MB + 25.6 MB); only valid for the default kernel / workload
-        traffic = 657.1e6 if (fused and args.planes == 'fp32' and os.environ.get('P3D_FUSED_IMPL', '') != 'v2') else None
+        # command (profiles/r1_final_ws_raw.csv: 630.5 MB + 22.3 MB); only valid for the default kernel / workload
+        traffic = 652.7e6 if (fused and args.planes == 'fp32' and os.environ.get('P3D_FUSED_IMPL', '') != 'v2') else None
         roof.update({'frac': roof['achieved'] / roof['peak'], 'traffic': traffic,
                      'kernel': ('k_render_ws' if os.environ.get('P3D_FUSED_IMPL', '') != 'v2' else 'k_render_fused') if fused else 'k_sample_decode',
                      'kernel_ms_per_launch': kern_ms,
