@@ -1,0 +1,1 @@
+"""TEST INFRASTRUCTURE ONLY: CPU restatements of the reference algorithms (renderer, ops, volume query)."""

@@ -22,18 +22,14 @@ def sigma2density(sigma):
 
 
 def create_samples(N, cube_length):
-    """eg3d_metrics3d.py:70-92 with voxel_origin = [0,0,0]: note the float (un-floored) y / x indices."""
-    origin = np.array([0, 0, 0]) - cube_length / 2
+    """eg3d_metrics3d.py:70-92 with voxel_origin = [0,0,0].  z index = n % N; the y / x indices are the fp32 quotients
+    (n/N) % N and ((n/N)/N) % N - the reference never floors them; index * voxel_size + corner, all in fp32."""
+    corner = -cube_length / 2
     size = cube_length / (N - 1)
-    idx = torch.arange(0, N ** 3, 1, dtype=torch.int64)
-    s = torch.zeros(N ** 3, 3)
-    s[:, 2] = idx % N
-    s[:, 1] = (idx.float() / N) % N
-    s[:, 0] = ((idx.float() / N) / N) % N
-    s[:, 0] = s[:, 0] * size + origin[2]
-    s[:, 1] = s[:, 1] * size + origin[1]
-    s[:, 2] = s[:, 2] * size + origin[0]
-    return s.unsqueeze(0)
+    n = torch.arange(N ** 3, dtype=torch.int64)
+    q = n.float() / N
+    cols = [(q / N) % N, q % N, (n % N).float()]
+    return torch.stack([c * size + corner for c in cols], dim=-1).unsqueeze(0)
 
 
 def volume(planes, dec, opts, resolution, triplane_crop=None, cull_clouds=None, use_triplane=True):

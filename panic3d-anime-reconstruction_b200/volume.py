@@ -30,19 +30,19 @@ def sigma2density(sigma):
 
 
 def create_samples(N=256, voxel_origin=(0, 0, 0), cube_length=2.0):
-    """The reference lattice (eg3d_metrics3d.py:70-92) as a (1, N^3, 3) fp32 tensor on the CPU, same arithmetic:
-    z index = n % N (integer), y index = (float(n)/N) % N and x index = ((float(n)/N)/N) % N are NOT floored."""
-    voxel_origin = np.array(voxel_origin) - cube_length / 2
-    voxel_size = cube_length / (N - 1)
-    idx = torch.arange(0, N ** 3, 1, dtype=torch.int64)
-    samples = torch.zeros(N ** 3, 3)
-    samples[:, 2] = idx % N
-    samples[:, 1] = (idx.float() / N) % N
-    samples[:, 0] = ((idx.float() / N) / N) % N
-    samples[:, 0] = (samples[:, 0] * voxel_size) + voxel_origin[2]
-    samples[:, 1] = (samples[:, 1] * voxel_size) + voxel_origin[1]
-    samples[:, 2] = (samples[:, 2] * voxel_size) + voxel_origin[0]
-    return samples.unsqueeze(0), voxel_origin, voxel_size
+    """The reference lattice (eg3d_metrics3d.py:70-92) as a (1, N^3, 3) fp32 CPU tensor + (corner, voxel size).
+
+    Point n has z index n % N (integer) but its y and x "indices" are the un-floored fp32 quotients
+    (n / N) mod N and ((n / N) / N) mod N, so the lattice is sheared by a fraction of a voxel; each index is then
+    scaled by the voxel size and shifted to the cube corner in fp32.  Same values as the reference, bit for bit
+    (pinned by tests/test_volume_oracle_golden.py); ``p3d_volume_query`` generates the same points in-kernel."""
+    corner = np.asarray(voxel_origin, dtype=np.float64) - cube_length / 2
+    step = cube_length / (N - 1)
+    n = torch.arange(N ** 3, dtype=torch.int64)
+    row = n.to(torch.float32) / N                                   # fp32 quotient, never floored
+    index = torch.stack([torch.remainder(row / N, N), torch.remainder(row, N), torch.remainder(n, N).to(torch.float32)], dim=-1)
+    shift = torch.tensor([float(corner[2]), float(corner[1]), float(corner[0])], dtype=torch.float32)
+    return (index * step + shift).unsqueeze(0), corner, step
 
 
 def query_volume(planes, decoder, rendering_kwargs, resolution=256, triplane_crop=None, cull_clouds=None,
