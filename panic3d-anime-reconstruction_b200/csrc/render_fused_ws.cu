@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
         // ---- merge + transmittance + omega + per-ray outputs of ray rl of group n (renderer.py:289-301, ray_marcher.py:25-57)
         // (mscr, chunks [c0, c1), pair_bar, finish): at S = 96 the ray's warp merges the coarse chunks and its partner the fine
         // chunks into the same scratch; they meet at named barrier pair_bar and the ray's warp finishes alone
-        auto composite_ray = [&](int n, int rl, float* mscr, int c0, int c1, int pair_bar, bool finish) {
+        auto composite_ray = [&](int n, int rl, float* mscr, float* hx, int c0, int c1, int pair_bar, bool finish) {
             GroupState& st = sm.st[n & 3];
             SlotState& sl = sm.slot[n & 1];
             const long long ray = (long long)((int)blockIdx.x + n * (int)gridDim.x) * GR + rl;
@@ -612,10 +612,14 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             }
             if (pair_bar >= 0) asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
             else __syncwarp();
-            if (!finish) return;
+            // alpha / (1 - alpha + 1e-10) / interval midpoint and the per-chunk inclusive products.  With a partner the
+            // chunks are split the same way as the merge: the partner publishes its half (hx: al | inc | tm, 3 x L/2
+            // floats in ITS scratch) and both meet at the pair barrier once more.
             float al[L / 32], inc[L / 32], tm[L / 32];
 #pragma unroll
             for (int c = 0; c < L / 32; ++c) {
+                al[c] = 0.f; inc[c] = 1.f; tm[c] = 0.f;
+                if (pair_bar >= 0 && (c < c0 || c >= c1)) continue;
                 const int i = c * 32 + lane;
                 float alpha = 0.f, fac = 1.f, tmid = 0.f;
                 if (i < L - 1) {
@@ -628,7 +632,28 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
                 al[c] = alpha; inc[c] = fac; tm[c] = tmid;
             }
 #pragma unroll
-            for (int c = 0; c < L / 32; ++c) inc[c] = warp_scan_mul(inc[c], lane);   // independent chains
+            for (int c = 0; c < L / 32; ++c)
+                if (pair_bar < 0 || (c >= c0 && c < c1)) inc[c] = warp_scan_mul(inc[c], lane);   // independent chains
+            if (pair_bar >= 0) {
+                if (!finish) {
+#pragma unroll
+                    for (int c = 0; c < L / 32; ++c) {
+                        if (c < c0 || c >= c1) continue;
+                        const int j = (c - c0) * 32 + lane;
+                        hx[j] = al[c]; hx[L / 2 + j] = inc[c]; hx[L + j] = tm[c];
+                    }
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                if (!finish) return;
+#pragma unroll
+                for (int c = 0; c < L / 32; ++c) {
+                    if (c >= c0 && c < c1) continue;                                 // the partner's chunks [c1, L/32)
+                    const int j = (c - c1) * 32 + lane;
+                    al[c] = hx[j]; inc[c] = hx[L / 2 + j]; tm[c] = hx[L + j];
+                }
+            } else if (!finish) {
+                return;
+            }
             float carry = 1.f, acc_w = 0.f, acc_d = 0.f, wprev = 0.f;
 #pragma unroll
             for (int c = 0; c < L / 32; ++c) {
@@ -707,14 +732,14 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws(const WsArgs a) {
             ebar();
             if (kPreSig) {
                 if (e < kEW / 2) {
-                    if (e < GR) composite_ray(n, e, scr, 0, L / 64, 2 + e, true);
+                    if (e < GR) composite_ray(n, e, scr, sm.rscratch + (e + kEW / 2) * (2 * L), 0, L / 64, 2 + e, true);
                 } else {
                     const int rl = e - kEW / 2;
-                    if (rl < GR) composite_ray(n, rl, sm.rscratch + rl * (2 * L), L / 64, L / 32, 2 + rl, false);
+                    if (rl < GR) composite_ray(n, rl, sm.rscratch + rl * (2 * L), scr, L / 64, L / 32, 2 + rl, false);
                     sigmoid_in_place(n, 1);
                 }
             } else {
-                for (int rl = e; rl < GR; rl += kEW) composite_ray(n, rl, scr, 0, L / 32, -1, true);
+                for (int rl = e; rl < GR; rl += kEW) composite_ray(n, rl, scr, nullptr, 0, L / 32, -1, true);
             }
             ebar();
         };
