@@ -392,6 +392,9 @@ int p3d_render_forward(const p3d_render_params* p, const void* planes, const flo
                                  out_depth, out_wsum, out_xyz, (cudaStream_t)stream);
     if (p->mlp_mode == P3D_MLP_TC_3XBF16 || p->mlp_mode == P3D_MLP_TC_BF16) {
         static const char* impl = getenv("P3D_FUSED_IMPL");       // "v2": 2-CTA/SM bulk-synchronous kernel; default: warp-specialised
+        if (impl && impl[0] == 'v' && impl[1] == '5' && fused_ws3_supported(g))                 // experimental, opt-in only
+            return render_forward_fused_ws3(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
+                                            out_depth, out_wsum, out_xyz, (cudaStream_t)stream);
         if (!(impl && impl[0] == 'v' && impl[1] == '2') && fused_ws_supported(g))
             return render_forward_fused_ws(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
                                            out_depth, out_wsum, out_xyz, (cudaStream_t)stream);

@@ -64,6 +64,12 @@ int render_forward_fused(const Geom& g, const p3d_render_params* p, const void* 
                          const float* u_f, const Workspace& ws, float* out_rgb, float* out_depth, float* out_wsum,
                          float* out_xyz, cudaStream_t stream);
 // warp-specialised fused renderer (v3): 1 CTA/SM, gather / epilogue / ray / MMA roles, two ray groups in flight.
+// experimental pipeline-depth-3 variant (render_fused_ws3.cu): opt-in through P3D_FUSED_IMPL=v5, not validated on hardware yet
+bool fused_ws3_supported(const Geom& g);
+int render_forward_fused_ws3(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
+                             const float* w2, const float* b2, const float* ro, const float* rd, const float* u_c,
+                             const float* u_f, const Workspace& ws, float* out_rgb, float* out_depth, float* out_wsum,
+                             float* out_xyz, cudaStream_t stream);
 bool fused_ws_supported(const Geom& g);
 int render_forward_fused_ws(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
                             const float* w2, const float* b2, const float* ro, const float* rd, const float* u_c,
