@@ -1,5 +1,5 @@
-"""CPU: discrete-event simulation of the mbarrier protocol of the experimental pipeline-depth-3 renderer
-(csrc/render_fused_ws3.cu, P3D_FUSED_IMPL=v5).
+"""CPU: discrete-event simulation of the mbarrier protocols of the fused renderers - the experimental pipeline-depth-3
+kernel (csrc/render_fused_ws3.cu, P3D_FUSED_IMPL=v5) and the shipped one (csrc/render_fused_ws.cu).
 
 The kernel has never run on hardware (see its header), so this test checks what can be checked without a GPU: the pass
 schedule and the hand-off protocol between its 25 warps.  Every role's control flow is transcribed from the CUDA source
@@ -217,10 +217,13 @@ class Sim:
                     self.composite_done.add(n)
                 self.omega_ready[n & 1].arrive()
 
+    def procs(self):
+        return ([('G%d' % g, self.gather_warp(g)) for g in range(12)] + [('M', self.mma_thread())] +
+                [('E%d' % e, self.epilogue_warp(e)) for e in range(K_EW)] + [('R%d' % r, self.ray_warp(r)) for r in range(K_RW)])
+
     # ---------------------------------------------------------------- scheduler
     def run(self):
-        procs = ([('G%d' % g, self.gather_warp(g)) for g in range(12)] + [('M', self.mma_thread())] +
-                 [('E%d' % e, self.epilogue_warp(e)) for e in range(K_EW)] + [('R%d' % r, self.ray_warp(r)) for r in range(K_RW)])
+        procs = self.procs()
         state = {name: ('ready', None) for name, _ in procs}          # ready | wait(bar, parity) | sleep | ebar(gen) | done
         gens = dict(procs)
 
@@ -263,6 +266,151 @@ class Sim:
         assert self.colours_done == set(range(self.N))
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# the shipped kernel (csrc/render_fused_ws.cu): two groups in flight, per-ray phases on the epilogue warps
+# ------------------------------------------------------------------------------------------------------------------
+def tile_at_v3(q):                                   # render_fused_ws.cu: tile_at -  C(A) C(B) F(A) F(B) | ...
+    u, j = divmod(q, 12)
+    sub = j // 3
+    return (2 * u + (sub & 1), sub >> 1, j - sub * 3)
+
+
+class SimV3(Sim):
+    """Same machinery, protocol of the default kernel: schedule C(A) C(B) F(A) F(B), colour logits in two 6-tile slots,
+    importance / merge / colours inline on the eight epilogue warps (named barrier), sigma read-back deferred by one tile
+    except for the odd tail group, fine_ready / state_free with one arrival."""
+
+    def __init__(self, N, seed):
+        super().__init__(N, seed)
+        self.T = 12 * ((N + 1) // 2)
+        self.fine_ready = [Bar(1) for _ in range(4)]
+
+    def tiles(self):
+        return [t for t in (tile_at_v3(q) for q in range(self.T)) if t[0] < self.N]
+
+    def is_tail(self, td):
+        return (self.N & 1) and td[0] == self.N - 1 and td[1] == 0 and td[2] == 2
+
+    def gather_warp(self, gw):
+        team = gw >> 2
+        for my_it, (n, p, k) in enumerate(self.tiles()):
+            if my_it % K_TEAMS != team:
+                continue
+            if p == 0:
+                yield ('wait', self.state_free[n & 3], ((n >> 2) & 1) ^ 1)
+                prev = self.state_owner[n & 3]
+                assert prev is None or prev == n or prev in self.colours_done, f'state slot of group {prev} rewritten for {n}'
+                self.state_owner[n & 3] = n
+            else:
+                yield ('wait', self.fine_ready[n & 3], (n >> 2) & 1)
+                assert n in self.importance_done, f'fine gather of {n} before its importance sampling'
+            stage = my_it % K_NA
+            yield ('wait', self.a1_empty[stage], ((my_it // K_NA) & 1) ^ 1)
+            yield ('work', self.dur(5, 20))
+            self.a1_full[stage].arrive()
+
+    def mma_thread(self):
+        it, prev = 0, None
+
+        def layer2(it2, tp):
+            n, p, k = tp
+            buf = it2 & 1
+            yield ('wait', self.a2_full[buf], (it2 >> 1) & 1)
+            yield ('wait', self.dsig_empty, (it2 & 1) ^ 1)
+            area = (n & 1, p * 3 + k)
+            owner = self.area_owner.get(area)
+            assert owner is None or owner in self.colours_done, f'layer 2 of {tp} overwrites slot tile {area} of group {owner} before its colours'
+            assert not self.sig_unread, 'sigma accumulator overwritten before it was read'
+            self.area_owner[area] = n
+
+            def done():
+                self.tiles_written.setdefault(n, set()).add((p, k))
+                self.sig_unread = True
+                self.d2_full.arrive(); self.a2_empty[buf].arrive()
+            self.later(self.dur(0.2, 2), done)
+        for td in self.tiles():
+            stage = it % K_NA
+            yield ('wait', self.a1_full[stage], (it // K_NA) & 1)
+            yield ('wait', self.d1_empty, (it & 1) ^ 1)
+            assert not self.d1_unread, 'D1 overwritten before the epilogue read it'
+
+            def done1(stage=stage):
+                self.d1_unread = True
+                self.d1_full.arrive(); self.a1_empty[stage].arrive()
+            self.later(self.dur(0.2, 2), done1)
+            if prev is not None:
+                yield from layer2(it - 1, prev)
+            prev = td; it += 1
+            if self.is_tail(td):
+                yield from layer2(it - 1, prev)
+                prev = None
+        if prev is not None:
+            yield from layer2(it - 1, prev)
+
+    def epilogue_warp(self, e):
+        chunk, it, prev = e >> 2, 0, None
+
+        def sigma_read(it_prev, tp):
+            if chunk != 0:
+                return
+            yield ('wait', self.d2_full, it_prev & 1)
+            yield ('work', self.dur(0.2, 1))
+            self.sig_unread_readers = getattr(self, 'sig_unread_readers', 0) + 1
+            if self.sig_unread_readers == 4:
+                self.sig_unread_readers, self.sig_unread = 0, False
+            self.dsig_empty.arrive()
+
+        def after_sigma(tp):
+            n, p, k = tp
+            if k != 2:
+                return
+            if p == 0:                                                   # importance(n)
+                yield ('ebar',)
+                yield ('work', self.dur(2, 10))
+                yield ('ebar',)
+                if e == 0:
+                    self.importance_done.add(n)
+                    self.fine_ready[n & 3].arrive()
+            else:                                                        # composite(n); colours(n)
+                yield ('ebar',)
+                yield ('work', self.dur(2, 10))
+                yield ('ebar',)
+                assert self.tiles_written.get(n, set()) == {(pp, kk) for pp in (0, 1) for kk in range(3)}, f'colours({n}) before all six tiles'
+                yield ('work', self.dur(1, 6))
+                yield ('ebar',)
+                yield ('work', self.dur(0.1, 0.5))
+                yield ('ebar',)
+                if e == 0:
+                    self.colours_done.add(n)
+                    self.state_free[n & 3].arrive()
+        for td in self.tiles():
+            yield ('wait', self.d1_full, it & 1)
+            yield ('work', self.dur(0.2, 1))
+            self.d1_readers = getattr(self, 'd1_readers', 0) + 1
+            if self.d1_readers == K_EW:
+                self.d1_readers, self.d1_unread = 0, False
+            self.d1_empty.arrive()
+            buf = it & 1
+            yield ('wait', self.a2_empty[buf], ((it >> 1) & 1) ^ 1)
+            yield ('work', self.dur(1, 4))
+            self.a2_full[buf].arrive()
+            if prev is not None:
+                yield from sigma_read(it - 1, prev)
+                yield from after_sigma(prev)
+            prev = td; it += 1
+            if self.is_tail(td):
+                yield from sigma_read(it - 1, prev)
+                yield from after_sigma(prev)
+                prev = None
+        if prev is not None:
+            yield from sigma_read(it - 1, prev)
+            yield from after_sigma(prev)
+
+    def procs(self):
+        return ([('G%d' % g, self.gather_warp(g)) for g in range(12)] + [('M', self.mma_thread())] +
+                [('E%d' % e, self.epilogue_warp(e)) for e in range(K_EW)])
+
+
 def test_pass_schedule_visits_every_group_once_in_a_valid_order():
     for N in range(1, 12):
         seq = [pass_at(j, N) for j in range(2 * N)]
@@ -282,3 +430,21 @@ def test_pass_schedule_visits_every_group_once_in_a_valid_order():
 def test_protocol_has_no_deadlock_or_hazard(N):
     for seed in range(12):
         Sim(N, seed * 101 + N).run()
+
+
+@pytest.mark.parametrize('N', [1, 2, 3, 4, 5, 6, 7, 9, 12])
+def test_shipped_kernel_protocol_has_no_deadlock_or_hazard(N):
+    """The default kernel's hand-offs (validated on hardware for the sizes the GPU tests use) for every small group count,
+    odd and even - the odd tail group takes a different path through the sigma read-back."""
+    for seed in range(10):
+        SimV3(N, seed * 77 + N).run()
+
+
+def test_shipped_kernel_needs_its_odd_tail_flush():
+    """Sanity of the simulator itself: without the immediate sigma flush for an odd tail group the protocol deadlocks
+    (the group's fine tiles wait for importance depths that wait for a sigma nobody reads)."""
+    class NoFlush(SimV3):
+        def is_tail(self, td):
+            return False
+    with pytest.raises(AssertionError, match='deadlock'):
+        NoFlush(3, 1).run()
