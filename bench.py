@@ -33,6 +33,11 @@ FLOP_PER_SAMPLE = 2 * 32 * 64 + 2 * 64 * 33            # 8,320 tensor-eligible F
 BYTES_PER_VIEW = 3 * C * P * P * 4 + R * R * 37 * 4    # tri-plane read once + 37 floats/ray out
 
 
+# rendering_options of BASELINE configs[1] (train_eclustrousC.py:409-440 + eg3dc_v0.py:30-31,55-56)
+RENDER_OPTS = dict(box_warp=0.7, ray_start=0.5, ray_end=1.5, depth_resolution=96, depth_resolution_importance=96,
+                   disparity_space_sampling=False, clamp_mode='softplus', white_back=True, triplane_depth=1)
+
+
 def workload_config(n_gpus, mlp_mode='tc_3xbf16', planes='fp32'):
     return {'workload': f'{VIEWS} views/GPU x {R}x{R} rays x ({S}+{SF}) samples, {VIEWS} distinct 3x{C}x{P}x{P} fp32 tri-planes/GPU',
             'views_per_gpu': VIEWS, 'rays': R * R, 'samples_coarse': S, 'samples_importance': SF, 'plane': P,
@@ -174,7 +179,6 @@ def run_ours(args):
     from panic3d_b200.training.volumetric_rendering.renderer import ImportanceRenderer
     from panic3d_b200.training.volumetric_rendering.ray_sampler import RaySampler
     from panic3d_b200.training.triplane import OSGDecoder
-    from oracle import renderer_oracle as orc      # DEFAULT_OPTS table + (rank 0, N=1) the cpu_baseline leg
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -194,7 +198,7 @@ def run_ours(args):
                                                           azim=float(spin[(rank * VIEWS + i) % 12][1]), dist=1.0, fov=30.0)['camera_label']
                           for i in range(VIEWS)])
     labels_dev = labels.to(dev)
-    opts = dict(orc.DEFAULT_OPTS)
+    opts = dict(RENDER_OPTS)                     # the GPU arm never touches oracle/ (only cpu_reference_time does)
     renderer, sampler = ImportanceRenderer(use_triplane=True), RaySampler()
     renderer.mlp_mode = mlp_mode
     renderer.planes_bf16 = args.planes == 'bf16'
