@@ -4,8 +4,10 @@
 //   warps  0-11  GATHER    three teams of four warps; team j takes tiles j, j+3, ... of the tile sequence; a warp owns
 //                          32 rows of its tile: taps -> 12 x 128-bit loads per lane -> lerp -> bf16 hi/lo A1 tile
 //   warps 12-19  EPILOGUE  per tile: tcgen05.ld D1 -> softplus2 -> A2 tile; sigma read-back; after a group's coarse
-//                          pass the importance sampling, after its fine pass merge/transmittance and the colour
-//                          reduction straight out of TMEM (256 threads, named barrier 1)
+//                          pass the importance sampling, after its fine pass merge/transmittance (both as warp-per-ray
+//                          code; at S=96 warp r+4 is ray r's partner: it sorts the uniforms, merges the fine half and
+//                          turns the parked colour logits into colours in place in TMEM) and the colour reduction
+//                          straight out of TMEM (named barrier 1 = the eight warps, 2..5 = the ray/partner pairs)
 //   warp  20     MMA       one thread: layer-1 (N=64) and layer-2 (N=32 colour + N=16 sigma) tcgen05.mma, commits
 //
 // A ray group is 384/S rays (4 at S=Sf=96, 8 at 48); a pass over it is three full 128-row tiles, tile k holding
