@@ -101,68 +101,119 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# reference arm / cpu_baseline: the oracle port (torch CPU, the reference's own ATen op chain)
+# reference arm / cpu_baseline: the reference's own CPU implementation of the path, on the box's host cores.
+#   kind "reference": baseline/_ref holds the UNMODIFIED reference tree (installed by baseline/install_ref.sh in the build
+#                     container; git-ignored, shipped to the GPU box) -> its ImportanceRenderer / RaySampler / OSGDecoder are
+#                     imported exactly as SURVEY.md section 8c describes and timed on CPU
+#   kind "port":      no baseline/_ref -> the oracle restatement (torch CPU, the reference's own ATen op chain)
+# One step = ONE view of the 8-view workload (a bounded sample: ~2.4 s of CPU work; the metric is per view).
 # --------------------------------------------------------------------------------------------
-def cpu_reference_time(steps, warmup, views=1):
-    """Times oracle.render (gather='aten') on `views` view(s) of the bench workload per step."""
+REF_TREE = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def _import_reference():
+    """-> (ImportanceRenderer, RaySampler, OSGDecoder, camera_params_to_matrix) of the unmodified reference, or None."""
+    src = os.path.join(REF_TREE, '_train', 'eg3dc', 'src')
+    if not os.path.isdir(os.path.join(src, 'training', 'volumetric_rendering')):
+        return None
+    import types
+    os.environ.setdefault('PROJECT_DN', REF_TREE)
+    for q in (src, REF_TREE):
+        if q not in sys.path:
+            sys.path.insert(0, q)
+    sys.modules.setdefault('kornia', types.ModuleType('kornia'))          # only paste_front / the loss use it (SURVEY 8c)
+    try:
+        import training.triplane as ref_tp
+        from training.volumetric_rendering.renderer import ImportanceRenderer
+        from training.volumetric_rendering.ray_sampler import RaySampler
+        import _databacks.lustrous_renders_v1 as ref_dk
+    except Exception as e:                                                 # a broken install must not look like a fast reference
+        print(f'[bench] baseline/_ref present but not importable ({type(e).__name__}: {e}); timing the oracle port', file=sys.stderr)
+        return None
+    if 'baseline/_ref' not in os.path.abspath(sys.modules[ImportanceRenderer.__module__].__file__).replace(os.sep, '/'):
+        return None                                                       # our drop-in modules shadow these names: never time those as "reference"
+    return ImportanceRenderer, RaySampler, ref_tp.OSGDecoder, ref_dk.camera_params_to_matrix
+
+
+def cpu_reference_time(steps, warmup, views=1, cap_s=240.0):
+    """Times `views` view(s) of the bench workload per step on the host CPU: the imported reference when baseline/_ref
+    exists, else oracle.render (gather='aten').  Stops early once `cap_s` seconds of timed steps have accumulated.
+    -> (times, threads, kind)"""
     import torch
     from oracle import renderer_oracle as orc
     g = torch.Generator().manual_seed(0)
+    ref = _import_reference()
+    opts = dict(RENDER_OPTS)
+    planes = torch.randn(views, 3, C, P, P, generator=g)
+    w1, w2 = torch.randn(64, C, generator=g), torch.randn(33, 64, generator=g)
+    if ref is not None:
+        RefRenderer, RefSampler, RefDecoder, ref_cam = ref
+        renderer, sampler = RefRenderer(use_triplane=True), RefSampler()
+        decoder = RefDecoder(C, {'decoder_lr_mul': 1, 'decoder_output_dim': 32}).requires_grad_(False)
+        with torch.no_grad():
+            decoder.net[0].weight.copy_(w1); decoder.net[2].weight.copy_(w2)
+        labels = torch.stack([ref_cam('eg3d_lustrousB', elev=0.0, azim=-180.0 + 30.0 * i, dist=1.0, fov=30.0)['camera_label'] for i in range(views)])
+        c2w, K = labels[:, :16].view(-1, 4, 4), labels[:, 16:25].view(-1, 3, 3)
+
+        def render(res, u_c, u_f):                                        # the reference draws its own jitter (torch.rand_like)
+            ro, rd = sampler(c2w, K, res)
+            return renderer(planes if res == R else planes[:1], decoder, ro if res == R else ro[:1], rd if res == R else rd[:1], opts)
+    else:
+        dec = dict(w1=w1, b1=torch.zeros(64), w2=w2, b2=torch.zeros(33), lr_mul=1.0, force_sigmoid=False)
+        cams = [orc.camera_params_to_matrix(0.0, -180.0 + 30.0 * i, 1.0, 30.0) for i in range(views)]
+        c2w, K = torch.stack([c[0] for c in cams]), torch.stack([c[1] for c in cams])
+
+        def render(res, u_c, u_f):
+            ro, rd = orc.ray_sampler(c2w if res == R else c2w[:1], K if res == R else K[:1], res)
+            return orc.render(planes if res == R else planes[:1], dec, ro, rd, opts, u_c, u_f, use_triplane=True, gather='aten')
     # torch's CPU ops do not scale to every core of a 100+-core host on tensors this size: probe a
     # quarter-size render at a few thread counts and give the baseline the fastest one.
     ncpu = os.cpu_count() or 1
     cands = sorted({c for c in (ncpu, 64, 32, 16, 8) if c <= ncpu}, reverse=True)
+    best = (ncpu, 1e30)
     if len(cands) > 1:
-        pp = torch.randn(1, 3, C, P, P, generator=g)
-        pd = dict(w1=torch.randn(64, C, generator=g), b1=torch.zeros(64), w2=torch.randn(33, 64, generator=g), b2=torch.zeros(33))
-        pc2w, pK = (t[None] for t in orc.camera_params_to_matrix(0.0, 30.0, 1.0, 30.0))
         pu_c, pu_f = torch.rand(1, 64 * 64, S, 1, generator=g), torch.rand(64 * 64, SF, generator=g)
-        best = (None, 1e30)
         for c in cands:
             torch.set_num_threads(c)
             with torch.no_grad():
                 t0 = time.perf_counter()
-                pro, prd = orc.ray_sampler(pc2w, pK, 64)
-                orc.render(pp, pd, pro, prd, dict(orc.DEFAULT_OPTS), pu_c, pu_f, use_triplane=True, gather='aten')
+                render(64, pu_c, pu_f)
                 dt = time.perf_counter() - t0
             if dt < best[1]:
                 best = (c, dt)
-        torch.set_num_threads(best[0])
-    else:
-        torch.set_num_threads(ncpu)
-    planes = torch.randn(views, 3, C, P, P, generator=g)
-    dec = dict(w1=torch.randn(64, C, generator=g), b1=torch.zeros(64), w2=torch.randn(33, 64, generator=g), b2=torch.zeros(33),
-               lr_mul=1.0, force_sigmoid=False)
-    cams = [orc.camera_params_to_matrix(0.0, -180.0 + 30.0 * i, 1.0, 30.0) for i in range(views)]
-    c2w, K = torch.stack([c[0] for c in cams]), torch.stack([c[1] for c in cams])
-    opts = dict(orc.DEFAULT_OPTS)
+    torch.set_num_threads(best[0])
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             u_c = torch.rand(views, R * R, S, 1, generator=g)
             u_f = torch.rand(views * R * R, SF, generator=g)
             t0 = time.perf_counter()
-            ro, rd = orc.ray_sampler(c2w, K, R)
-            orc.render(planes, dec, ro, rd, opts, u_c, u_f, use_triplane=True, gather='aten')
+            render(R, u_c, u_f)
             dt = time.perf_counter() - t0
             if i >= warmup:
                 times.append(dt)
-    return times, torch.get_num_threads()
+                if sum(times) > cap_s:
+                    break
+    return times, torch.get_num_threads(), ('reference' if ref is not None else 'port')
 
 
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
-    times, cores = cpu_reference_time(steps, warmup, views=1)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    times, cores, kind = cpu_reference_time(steps, warmup, views=1)
     total = sum(times)
     v = len(times) / total
-    sample = f'{len(times)} timed steps x 1 view of the workload (128x128 rays, 96+96 samples, 512^2 planes) after {warmup} warm-up'
+    what = ('the unmodified reference ImportanceRenderer.forward imported from baseline/_ref' if kind == 'reference'
+            else 'the oracle port (oracle/renderer_oracle.py, the reference\'s ATen op chain)')
+    sample = (f'{what} on the host CPU, {cores} threads; each step = 1 of the workload\'s 8 views (128x128 rays, 96+96 samples, '
+              f'512^2 planes; views/s is per view); {len(times)} timed steps after {warmup} warm-up'
+              + ('' if len(times) == steps else f' (stopped at the 240 s cap, {steps} requested)'))
     out = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(times),
            'warmup': warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
-           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.gpus, 'cpu'),
-           'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+           'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args.gpus, args.mlp, args.planes),
+           'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': kind, 'sample': sample},
            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}
     print(json.dumps(out), flush=True)
 
@@ -312,6 +363,34 @@ def run_ours(args):
                 variants['training fwd+bwd (4 views, 64^2 rays, 48+48, 256^2 planes)'] = {'value': round(v0.elapsed_time(v1) / 10, 3), 'unit': 'ms/step', 'steps': 10}
                 del tp, tdec, rt
             torch.cuda.empty_cache()
+        # ---- the reference's own GPU path beside ours: the UNMODIFIED ImportanceRenderer from baseline/_ref - ~60
+        #      eager PyTorch CUDA ops per pass - on this same GPU, same planes / decoder / cameras, one view per call
+        #      (its intermediates are ~15 GB per view; views/s is per view)
+        if variants is not None:
+            ref = _import_reference()
+            if ref is not None:
+                RefRenderer, RefSampler, RefDecoder, _cam = ref
+                rr, rs = RefRenderer(use_triplane=True).to(dev), RefSampler()
+                rdec = RefDecoder(C, {'decoder_lr_mul': 1, 'decoder_output_dim': 32}).to(dev).requires_grad_(False)
+                rdec.load_state_dict(decoder.state_dict())
+                c2w1, K1 = labels_dev[:1, :16].view(-1, 4, 4), labels_dev[:1, 16:25].view(-1, 3, 3)
+
+                def rstep():
+                    ro, rd = rs(c2w1, K1, R)
+                    return rr(planes[:1], rdec, ro, rd, opts)
+                for _ in range(2):
+                    rstep()
+                v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                torch.cuda.synchronize()
+                v0.record()
+                for _ in range(5):
+                    rstep()
+                v1.record()
+                torch.cuda.synchronize()
+                variants['reference renderer (unmodified, eager PyTorch) on this GPU, 1 view/call'] = {
+                    'value': round(5 / (v0.elapsed_time(v1) * 1e-3), 2), 'unit': UNIT, 'steps': 5}
+                del rr, rdec
+                torch.cuda.empty_cache()
         # ---- e2e through the host-buffer C-ABI entry point (pinned host planes in, images out)
         e2e = None
         if not args.no_e2e:
@@ -362,9 +441,11 @@ def run_ours(args):
         if variants:
             out['variants'] = variants
         if world == 1 and not args.no_cpu_baseline:
-            times, cores = cpu_reference_time(steps=3, warmup=1, views=1)
-            out['cpu_baseline'] = {'value': len(times) / sum(times), 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                                   'sample': '3 timed renders of 1 view of the same workload (oracle port, torch CPU, all cores) after 1 warm-up'}
+            times, cores, kind = cpu_reference_time(steps=3, warmup=1, views=1)
+            out['cpu_baseline'] = {'value': len(times) / sum(times), 'unit': UNIT, 'cores': cores, 'kind': kind,
+                                   'sample': f'{len(times)} timed renders of 1 view of the same workload ('
+                                             + ('unmodified reference from baseline/_ref' if kind == 'reference' else 'oracle port')
+                                             + f', torch CPU, {cores} threads) after 1 warm-up'}
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()

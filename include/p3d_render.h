@@ -110,6 +110,13 @@ int p3d_raygen_ortho(const float* rot, const float* dist, int32_t n_views, int32
 /* Scratch needed by p3d_render_forward for these params (bytes). */
 size_t p3d_render_workspace_bytes(const p3d_render_params* p);
 
+/* 1 when the fused tcgen05 renderer (mlp_mode P3D_MLP_TC_*) has a kernel for these params
+   (depth_resolution == depth_resolution_importance in {48, 96}, C=32, hidden 64, out 33, rays per view a multiple of
+   384/S, 32-bit tap offsets), else 0: such configurations run on the fp32 SIMT kernels (P3D_MLP_FP32_SIMT).  The host
+   mirror (ImportanceRenderer.mlp_mode = 'auto') uses this to pick the tensor-core path whenever it exists; an
+   explicit P3D_MLP_TC_* request for an unsupported configuration still fails with P3D_EUNSUPPORTED. */
+int p3d_render_fused_supported(const p3d_render_params* p);
+
 /* ImportanceRenderer.forward, volumetric_rendering/renderer.py:162-264
    (= sample_stratified :303-326, run_model :266-280 [sample_from_planes :68-81 + OSGDecoder
    triplane.py:528-544], crop/cull masks :138-153, MipRayMarcher2 ray_marcher.py:25-57,
@@ -159,6 +166,19 @@ int p3d_decode_points(const p3d_render_params* p, const void* planes,
                       const float* w1, const float* b1, const float* w2, const float* b2,
                       const float* coords, int64_t n_points_per_view,
                       float* out_rgb, float* out_sigma, void* stream);
+
+/* Backward of p3d_decode_points (first order): what the density-regularisation phase of the training loop needs
+   (loss_orthocondA.py:579-600: G.sample_mixed(...)['sigma'] -> TVloss.backward(); triplane.py:283-298 -> run_model).
+   Gradients flow to the tri-plane features and the four decoder tensors; the coordinates are constants (they carry
+   no grad in the reference's call).  planes: channels-last texels addressed by the strides in *p (read only);
+     g_rgb (N,K,out_dim-1), g_sigma (N,K)   incoming gradients (pass zeros for an output the loss does not use)
+     d_planes (N,3,H,W,C) contiguous fp32, d_w1, d_b1, d_w2, d_b2: ZERO-INITIALISED by the caller, accumulated with
+     atomics; parameter gradients are w.r.t. the raw tensors (gains folded in). */
+int p3d_decode_points_backward(const p3d_render_params* p, const void* planes,
+                               const float* w1, const float* b1, const float* w2, const float* b2,
+                               const float* coords, int64_t n_points_per_view,
+                               const float* g_rgb, const float* g_sigma,
+                               float* d_planes, float* d_w1, float* d_b1, float* d_w2, float* d_b2, void* stream);
 
 /* Dense sigma / colour grid for mesh extraction: the renderer-level part of get_eg3d_volume
    (_util/eg3d_metrics3d.py:94-183), which the reference evaluates as 168 host-side chunks of 100k points through

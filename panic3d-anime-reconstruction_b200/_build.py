@@ -61,6 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError('nvcc failed on %s' % os.path.basename(src))
         if verbose:
             print(out)
+    os.makedirs(os.path.dirname(LIB), exist_ok=True)       # lib/ holds only ignored artefacts: a fresh clone has no such directory
     tmp = LIB + '.tmp.%d' % os.getpid()
     r = subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', tmp] + objs,
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)

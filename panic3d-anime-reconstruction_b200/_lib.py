@@ -9,7 +9,8 @@ import os
 import threading
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, 'lib', 'libp3d.so')
+# P3D_LIBP3D: load another build of the library (A/B experiments: profiles/experiments/build_variants.py); default in-tree
+LIB_PATH = os.environ.get('P3D_LIBP3D') or os.path.join(PKG, 'lib', 'libp3d.so')
 
 P3D_PLANES_EG3D, P3D_PLANES_PANIC3D = 0, 1
 P3D_RAYS_NUMERIC, P3D_RAYS_AUTOBOX = 0, 1
@@ -47,8 +48,10 @@ _PROTOS = {
     'p3d_raygen_pinhole': (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, _VP, _VP, _VP]),
     'p3d_raygen_ortho': (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_double, _VP, _VP, _VP]),
     'p3d_render_workspace_bytes': (C.c_size_t, [C.POINTER(RenderParams)]),
+    'p3d_render_fused_supported': (C.c_int, [C.POINTER(RenderParams)]),
     'p3d_render_forward': (C.c_int, [C.POINTER(RenderParams)] + [_VP] * 9 + [_VP, C.c_size_t] + [_VP] * 5),
     'p3d_decode_points': (C.c_int, [C.POINTER(RenderParams)] + [_VP] * 6 + [C.c_int64, _VP, _VP, _VP]),
+    'p3d_decode_points_backward': (C.c_int, [C.POINTER(RenderParams)] + [_VP] * 6 + [C.c_int64] + [_VP] * 7 + [_VP]),
     'p3d_volume_query': (C.c_int, [C.POINTER(RenderParams)] + [_VP] * 5 + [C.c_int32, C.c_double, C.c_double, C.c_double] + [_VP] * 5),
     'p3d_render_forward_host': (C.c_int, [C.POINTER(RenderParams)] + [_VP] * 7 + [C.c_int32] + [_VP] * 6),
     'p3d_render_backward_scratch_bytes': (C.c_size_t, [C.POINTER(RenderParams)]),

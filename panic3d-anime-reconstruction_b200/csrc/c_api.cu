@@ -369,6 +369,12 @@ size_t p3d_render_workspace_bytes(const p3d_render_params* p) {
     return workspace_layout(p, nullptr, nullptr);
 }
 
+int p3d_render_fused_supported(const p3d_render_params* p) {
+    Geom g;
+    if (!p || make_geom(p, &g)) return 0;
+    return fused_ws_supported(g) ? 1 : 0;
+}
+
 int p3d_render_forward(const p3d_render_params* p, const void* planes, const float* w1, const float* b1, const float* w2,
                        const float* b2, const float* ray_origins, const float* ray_dirs, const float* u_coarse,
                        const float* u_fine, void* workspace, size_t workspace_bytes, float* out_rgb, float* out_depth,
@@ -451,6 +457,21 @@ int p3d_decode_points(const p3d_render_params* p, const void* planes, const floa
     if ((long long)g.N * n_points_per_view == 0) return P3D_OK;
     P3D_REQUIRE(planes && w1 && b1 && w2 && b2 && coords && out_rgb && out_sigma, "null pointer");
     return decode_points_v1(g, p, planes, w1, b1, w2, b2, coords, n_points_per_view, out_rgb, out_sigma, (cudaStream_t)stream);
+}
+
+int p3d_decode_points_backward(const p3d_render_params* p, const void* planes, const float* w1, const float* b1, const float* w2,
+                               const float* b2, const float* coords, int64_t n_points_per_view, const float* g_rgb,
+                               const float* g_sigma, float* d_planes, float* d_w1, float* d_b1, float* d_w2, float* d_b2,
+                               void* stream) {
+    Geom g;
+    int rc = make_geom(p, &g);
+    if (rc) return rc;
+    P3D_REQUIRE(n_points_per_view >= 0, "negative point count");
+    if ((long long)g.N * n_points_per_view == 0) return P3D_OK;
+    P3D_REQUIRE(planes && w1 && b1 && w2 && b2 && coords && g_rgb && g_sigma, "null input pointer (pass zeros for an unused gradient)");
+    P3D_REQUIRE(d_planes && d_w1 && d_b1 && d_w2 && d_b2, "null output pointer");
+    return decode_points_backward_v1(g, p, planes, w1, b1, w2, b2, coords, n_points_per_view, g_rgb, g_sigma, d_planes, d_w1,
+                                     d_b1, d_w2, d_b2, (cudaStream_t)stream);
 }
 
 int p3d_volume_query(const p3d_render_params* p, const void* planes, const float* w1, const float* b1, const float* w2,

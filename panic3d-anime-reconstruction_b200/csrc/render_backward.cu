@@ -165,6 +165,11 @@ struct SampleBwdArgs {
     float *d_w1, *d_b1, *d_w2, *d_b2;   // gradients w.r.t. the RAW parameters (gains folded in)
     long long total;
     int per_ray;
+    // point-query mode (run_model backward, renderer.py:266-280): positions come from `coords` (N,K,3), the incoming
+    // gradients are per point - dsig = g_sigma (N,K), g_col = g_rgb (N,K,32) - and there are no masks and no omega
+    const float* coords;
+    const float* g_col;
+    long long per_view;
 };
 
 constexpr int kXs = 33, kHs = 65, kDs = 36;
@@ -226,14 +231,19 @@ __global__ void __launch_bounds__(kT) k_sample_backward(const SampleBwdArgs a) {
             const bool ok = gidx < a.total;
             float py = 0.f;
             if (ok) {
-                const long long ray = gidx / a.per_ray;
-                view = (int)(ray / g.M);
-                const float tval = a.depth[gidx];
-                const float* o = a.ro + ray * 3;
-                const float* d = a.rd + ray * 3;
-                px = __fadd_rn(o[0], __fmul_rn(tval, d[0]));
-                py = __fadd_rn(o[1], __fmul_rn(tval, d[1]));
-                pz = __fadd_rn(o[2], __fmul_rn(tval, d[2]));
+                if (a.coords) {
+                    view = (int)(gidx / a.per_view);
+                    px = a.coords[gidx * 3]; py = a.coords[gidx * 3 + 1]; pz = a.coords[gidx * 3 + 2];
+                } else {
+                    const long long ray = gidx / a.per_ray;
+                    view = (int)(ray / g.M);
+                    const float tval = a.depth[gidx];
+                    const float* o = a.ro + ray * 3;
+                    const float* d = a.rd + ray * 3;
+                    px = __fadd_rn(o[0], __fmul_rn(tval, d[0]));
+                    py = __fadd_rn(o[1], __fmul_rn(tval, d[1]));
+                    pz = __fadd_rn(o[2], __fmul_rn(tval, d[2]));
+                }
                 f = gather_features<BF16>(a.planes, g, view, px, py, pz, qd);
             }
             if (qd < 3) {                                         // lanes 0..2 of a sample record plane qd's taps
@@ -275,15 +285,16 @@ __global__ void __launch_bounds__(kT) k_sample_backward(const SampleBwdArgs a) {
         }
         float dsg = 0.f, om = 0.f;
         long long ray = 0;
-        if (live) { dsg = a.dsig[gidx]; om = a.omega[gidx]; ray = gidx / a.per_ray; }
-        // a density overwritten by a crop/cull/binarize mask is a constant of the reference graph
-        if (apply_masks(g, o[0], s_xz[tid * 2], s_xz[tid * 2 + 1]) != o[0]) dsg = 0.f;
+        const bool pts = a.coords != nullptr;
+        if (live) { dsg = a.dsig[gidx]; if (!pts) { om = a.omega[gidx]; ray = gidx / a.per_ray; } }
+        // a density overwritten by a crop/cull/binarize mask is a constant of the reference graph (run_model has no masks)
+        if (!pts && apply_masks(g, o[0], s_xz[tid * 2], s_xz[tid * 2 + 1]) != o[0]) dsg = 0.f;
         float dlog[kOut];
         dlog[0] = dsg;
 #pragma unroll
         for (int c = 0; c < kRgb; ++c) {
             const float sgm = sigmoid_t(o[1 + c]);
-            const float dcol = live ? 2.f * om * a.g_rgb[ray * kRgb + c] : 0.f;          // d rgb / d c_j = 2 * omega_j
+            const float dcol = !live ? 0.f : (pts ? a.g_col[gidx * kRgb + c] : 2.f * om * a.g_rgb[ray * kRgb + c]);   // d rgb / d c_j = 2 * omega_j
             dlog[1 + c] = dcol * (g.force_sigmoid ? 1.f : 1.002f) * sgm * (1.f - sgm);
         }
 #pragma unroll
@@ -430,6 +441,24 @@ int render_backward_v1(const Geom& g, const p3d_render_params* p, const void* pl
         kern<<<(unsigned)blocks, kT, smem, stream>>>(sa);
         P3D_LAUNCH_CHECK();
     }
+    return P3D_OK;
+}
+
+int decode_points_backward_v1(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
+                              const float* w2, const float* b2, const float* coords, long long n_pts, const float* g_rgb,
+                              const float* g_sigma, float* d_planes, float* d_w1, float* d_b1, float* d_w2, float* d_b2,
+                              cudaStream_t stream) {
+    const size_t smem = kBwdSmemFloats * sizeof(float);
+    auto kern = p->planes_bf16 ? k_sample_backward<true> : k_sample_backward<false>;
+    P3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SampleBwdArgs sa{};
+    sa.g = g; sa.planes = planes; sa.w1 = w1; sa.b1 = b1; sa.w2 = w2; sa.b2 = b2;
+    sa.coords = coords; sa.dsig = g_sigma; sa.g_col = g_rgb; sa.per_view = n_pts; sa.per_ray = 1;
+    sa.d_planes = d_planes; sa.d_w1 = d_w1; sa.d_b1 = d_b1; sa.d_w2 = d_w2; sa.d_b2 = d_b2;
+    sa.total = (long long)g.N * n_pts;
+    const long long blocks = (sa.total + kT - 1) / kT;
+    kern<<<(unsigned)blocks, kT, smem, stream>>>(sa);
+    P3D_LAUNCH_CHECK();
     return P3D_OK;
 }
 

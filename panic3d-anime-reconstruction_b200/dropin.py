@@ -77,10 +77,19 @@ class _PlaneMemo:
     (``ws`` is (N,14,512): one tiny device compare per call).  Strong references to the key tensors are held so that a
     freed-and-reallocated buffer can never alias a stale entry.  Training is untouched: calls under autograd
     (``torch.is_grad_enabled()`` with any input requiring grad), with ``update_emas=True`` or with non-'const' noise
-    bypass the memo."""
+    bypass the memo.
 
-    def __init__(self, synthesis):
+    Noise: ``G.f`` / ``G.synthesis`` never pass ``noise_mode``, so in the reference every call draws fresh
+    ``SynthesisLayer`` noise (``networks_stylegan2.py:334-343``: default 'random') - each view of a sweep sees slightly
+    different tri-planes.  Replaying one stochastic draw for all views would be neither the reference's behaviour nor
+    deterministic, so the memo does one of two explicit things with a call that leaves ``noise_mode`` out:
+    ``default_noise_mode='const'`` (what ``enable_plane_reuse`` sets up, a DELIBERATE, documented deviation: the whole
+    sweep is rendered from the const-noise tri-planes, deterministic and cacheable) passes that mode on to the backbone;
+    ``default_noise_mode=None`` leaves the call untouched and treats it as 'random' = not cacheable."""
+
+    def __init__(self, synthesis, default_noise_mode='const'):
         self.synthesis = synthesis
+        self.default_noise_mode = default_noise_mode
         self.key = None
         self.planes = None
         self.hits = self.misses = 0
@@ -116,8 +125,10 @@ class _PlaneMemo:
 
     def __call__(self, ws, cond=None, *args, **kwargs):
         import torch
+        if 'noise_mode' not in kwargs and self.default_noise_mode is not None:
+            kwargs = dict(kwargs, noise_mode=self.default_noise_mode)
         tensors = self._tensors([ws, cond, list(args), kwargs], [])
-        cacheable = (not kwargs.get('update_emas', False) and kwargs.get('noise_mode', 'const') == 'const'
+        cacheable = (not kwargs.get('update_emas', False) and kwargs.get('noise_mode', 'random') in ('const', 'none')
                      and not kwargs.get('return_more', False)
                      and not (torch.is_grad_enabled() and any(t.requires_grad for t in tensors)))
         scalars = repr(sorted((k, v) for k, v in kwargs.items() if not isinstance(v, (torch.Tensor, dict, list, tuple))))
@@ -137,13 +148,16 @@ class _PlaneMemo:
         self.key = self.planes = None
 
 
-def enable_plane_reuse(G):
+def enable_plane_reuse(G, default_noise_mode='const'):
     """Wrap ``G.backbone.synthesis`` with a one-entry memo (see ``_PlaneMemo``); idempotent.  Returns the memo
     (``.hits`` / ``.misses`` / ``.clear()``).  With it, a 16-view sweep of one subject through unchanged ``G.f`` runs the
-    backbone once, and the renderer's channels-last layout pass once (its plane cache keys on the same tensor)."""
+    backbone once, and the renderer's channels-last layout pass once (its plane cache keys on the same tensor).
+    ``default_noise_mode``: the noise mode given to backbone calls that do not name one ('const': deterministic sweep,
+    cacheable - differs from the reference, which redraws the layer noise for every view; None: keep the reference's
+    per-call random noise, in which case only calls that explicitly ask for 'const' / 'none' are cached)."""
     syn = G.backbone.synthesis
     if isinstance(syn, _PlaneMemo):
         return syn
-    memo = _PlaneMemo(syn)
+    memo = _PlaneMemo(syn, default_noise_mode)
     G.backbone.synthesis = memo
     return memo

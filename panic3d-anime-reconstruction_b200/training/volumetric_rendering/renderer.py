@@ -116,6 +116,7 @@ class _RenderFunction(torch.autograd.Function):
         return tuple(out)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable     # hand-written first-order backward: a double backward must raise, not silently treat it as constant
     def backward(ctx, g_rgb, g_depth, g_wsum, g_xyz):
         planes_cl, w1, b1, w2, b2, ro, rd, ws, depth = ctx.saved_tensors
         p, dev, L = ctx.p, planes_cl.device, _lib.lib()
@@ -136,6 +137,54 @@ class _RenderFunction(torch.autograd.Function):
                 d_w[3].to(dts[4]), None, None, None, None)
 
 
+class _PointsFunction(torch.autograd.Function):
+    """run_model under autograd (the Greg phase: loss_orthocondA.py:579-600 back-propagates a TV loss on
+    G.sample_mixed(...)['sigma']; triplane.py:283-298 -> renderer.run_model).  Forward = p3d_decode_points, backward =
+    p3d_decode_points_backward: gradients reach the tri-planes and the four decoder tensors; the query coordinates are
+    constants (they carry no grad in the reference's call)."""
+
+    @staticmethod
+    def forward(ctx, planes, w1, b1, w2, b2, coords, p):
+        dev = planes.device
+        L = _lib.lib()
+        N, K = coords.shape[0], coords.shape[1]
+        src = planes.detach().float()
+        srcc = src if src.is_contiguous() else src.contiguous()
+        planes_cl = torch.empty((N, 3, p.plane_h, p.plane_w, p.channels), device=dev, dtype=torch.float32)
+        _lib.check(L.p3d_planes_to_channels_last(srcc.data_ptr(), planes_cl.data_ptr(), N * 3, p.channels, p.plane_h, p.plane_w, 0,
+                                                 _lib.stream_ptr(dev)))
+        sv, sp, sr, sc, _ = planes_cl.stride()
+        p.stride_view, p.stride_plane, p.stride_row, p.stride_col, p.planes_bf16 = sv, sp, sr, sc, 0
+        wt = [t.detach().float().contiguous() for t in (w1, b1, w2, b2)]
+        coords = coords.detach().float().contiguous()
+        rgb = torch.empty((N, K, p.out_dim - 1), device=dev, dtype=torch.float32)
+        sigma = torch.empty((N, K, 1), device=dev, dtype=torch.float32)
+        _lib.check(L.p3d_decode_points(C.byref(p), planes_cl.data_ptr(), *[t.data_ptr() for t in wt], coords.data_ptr(), K,
+                                       rgb.data_ptr(), sigma.data_ptr(), _lib.stream_ptr(dev)))
+        ctx.save_for_backward(planes_cl, *wt, coords)
+        ctx.p = p
+        ctx.in_dtypes = (planes.dtype, w1.dtype, b1.dtype, w2.dtype, b2.dtype)
+        return rgb, sigma
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g_rgb, g_sigma):
+        planes_cl, w1, b1, w2, b2, coords = ctx.saved_tensors
+        p, dev, L = ctx.p, planes_cl.device, _lib.lib()
+        N, K = coords.shape[0], coords.shape[1]
+        g_rgb = torch.zeros((N, K, p.out_dim - 1), device=dev) if g_rgb is None else g_rgb.float().contiguous()
+        g_sigma = torch.zeros((N, K, 1), device=dev) if g_sigma is None else g_sigma.float().contiguous()
+        d_planes = torch.zeros_like(planes_cl)
+        d_w = [torch.zeros_like(t) for t in (w1, b1, w2, b2)]
+        with torch.cuda.device(dev):
+            _lib.check(L.p3d_decode_points_backward(C.byref(p), planes_cl.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(),
+                                                    b2.data_ptr(), coords.data_ptr(), K, g_rgb.data_ptr(), g_sigma.data_ptr(),
+                                                    d_planes.data_ptr(), *[t.data_ptr() for t in d_w], _lib.stream_ptr(dev)))
+        dts = ctx.in_dtypes
+        return (d_planes.permute(0, 1, 4, 2, 3).to(dts[0]), d_w[0].to(dts[1]), d_w[1].to(dts[2]), d_w[2].to(dts[3]), d_w[3].to(dts[4]),
+                None, None)
+
+
 class ImportanceRenderer(torch.nn.Module):
     """Reference: renderer.py:156-387.  Parameter-free, like the reference."""
 
@@ -144,7 +193,11 @@ class ImportanceRenderer(torch.nn.Module):
         self.ray_marcher = MipRayMarcher2()
         self.use_triplane = bool(use_triplane)
         self.plane_axes = generate_planes(use_triplane=use_triplane)
-        self.mlp_mode = _lib.P3D_MLP_FP32_SIMT     # decoder arithmetic (see include/p3d_render.h)
+        # decoder arithmetic (include/p3d_render.h).  'auto' (default): the fused tcgen05 kernel in its fp32-class 3-pass
+        # mode wherever it exists (p3d_render_fused_supported: depth_resolution == depth_resolution_importance in
+        # {48, 96} - the reference's training and eval settings), the fp32 SIMT kernels for every other sample count.
+        # An explicit _lib.P3D_MLP_* value forces that mode and raises if it has no kernel.
+        self.mlp_mode = 'auto'
         self.planes_bf16 = False                   # fast-mode plane storage
         self.injected_noise = None                 # (u_coarse (N,M,S[,1]), u_fine (N*M,Sf)) for parity tests
         # multi-GPU: callable(bounds2: cuda float tensor [min,max]) reducing the depth-clamp bounds across ranks in
@@ -187,7 +240,12 @@ class ImportanceRenderer(torch.nn.Module):
         p.binarize_clouds = float(binarize_clouds or 0)
         p.w1_gain, p.b1_gain, p.w2_gain, p.b2_gain = g1, gb1, g2, gb2
         p.force_sigmoid = 1 if force_sigmoid else 0
-        p.mlp_mode = int(self.mlp_mode)
+        if self.mlp_mode == 'auto':
+            p.mlp_mode = _lib.P3D_MLP_TC_3XBF16
+            if not _lib.lib().p3d_render_fused_supported(C.byref(p)):
+                p.mlp_mode = _lib.P3D_MLP_FP32_SIMT
+        else:
+            p.mlp_mode = int(self.mlp_mode)
         p.seed = int(torch.empty((), dtype=torch.int64).random_().item()) & 0xFFFFFFFFFFFFFFFF
         return p, (w1, b1, w2, b2)
 
@@ -290,11 +348,21 @@ class ImportanceRenderer(torch.nn.Module):
     def run_model(self, planes, decoder, sample_coordinates, sample_directions, options):
         """-> {'rgb' (N,K,32), 'sigma' (N,K,1), 'xyz'}.  Reference renderer.py:266-280."""
         self._require_cuda(planes, sample_coordinates)
-        if torch.is_grad_enabled() and (planes.requires_grad or sample_coordinates.requires_grad
-                                        or any(q.requires_grad for q in decoder.parameters())):
-            raise NotImplementedError('run_model backward is not implemented yet; call under torch.no_grad()')
         dev = planes.device
         N, K, _ = sample_coordinates.shape
+        if torch.is_grad_enabled() and sample_coordinates.requires_grad:
+            raise NotImplementedError('run_model: gradients w.r.t. the query coordinates are not implemented (no caller of the '
+                                      'reference needs them; planes and decoder parameters are differentiable)')
+        if torch.is_grad_enabled() and (planes.requires_grad or any(q.requires_grad for q in decoder.parameters())):
+            if planes.dim() != 5 or planes.shape[1] != 3:
+                raise ValueError(f'planes must be (N,3,C,H,W), got {tuple(planes.shape)}')
+            with torch.cuda.device(dev):
+                opts = dict(options)
+                opts.setdefault('depth_resolution', 2)
+                shape_probe = torch.empty((N, 3, planes.shape[3], planes.shape[4], planes.shape[2]), device='meta')
+                p, (w1, b1, w2, b2) = self._params(shape_probe, N, 0, opts, decoder, None, None, None)
+                rgb, sigma = _PointsFunction.apply(planes, w1, b1, w2, b2, sample_coordinates, p)
+            return {'rgb': rgb, 'sigma': sigma, 'xyz': sample_coordinates}
         with torch.cuda.device(dev):
             planes_cl = self._planes_cl(planes.detach())
             opts = dict(options)

@@ -52,6 +52,18 @@ RENDER_CASES = {
     # eval sampling 96+96 (eg3dc_v0.py:30-31) on a small image
     'mid_eval96': dict(seed=24, N=1, R=24, P=128, opts=_opts(), cameras=[(0.0, 0.0, 1.0, 30.0)],
                        triplane_crop=0.1, cull_clouds=0.5, force_sigmoid=True, sigma_bias=2.0),
+    # ---- fused tcgen05 kernel coverage (it exists for S = Sf in {48, 96} only): the option matrix of the small_* cases at 48+48
+    'fused48_ortho': _small(51, ortho=True, cameras=[(20.0, -135.0, 1.0, -1.0)], opts=dict(depth_resolution=48, depth_resolution_importance=48)),
+    'fused48_auto_limits': _small(52, opts=dict(ray_start='auto', ray_end='auto', depth_resolution=48, depth_resolution_importance=48)),
+    'fused48_disparity': _small(53, opts=dict(disparity_space_sampling=True, depth_resolution=48, depth_resolution_importance=48)),
+    'fused48_black_eg3dplanes': _small(54, use_triplane=False, opts=dict(white_back=False, depth_resolution=48, depth_resolution_importance=48)),
+    'fused48_shared_planes': _small(55, N=2, share_planes=True, cameras=[(0.0, 0.0, 1.0, 30.0), (0.0, 150.0, 1.0, 30.0)],
+                                    opts=dict(depth_resolution=48, depth_resolution_importance=48)),
+    'fused48_binarize': _small(56, binarize_clouds=0.5, triplane_crop=0.05, sigma_bias=1.0, opts=dict(depth_resolution=48, depth_resolution_importance=48)),
+    'fused96_lrmul_black': _small(57, lr_mul=0.5, opts=dict(white_back=False, depth_resolution=96, depth_resolution_importance=96)),
+    # BASELINE.json configs[1] (the benchmarked workload) at N=2: 128x128 rays, 96+96 samples, 512^2 planes, no cull ->
+    # strict tolerance.  The fixture keeps every 8th ray of the reference output (store_stride) to stay under 1 MB.
+    'headline96': dict(seed=58, N=2, R=128, P=512, opts=_opts(), cameras=[(0.0, -150.0, 1.0, 30.0), (0.0, 60.0, 1.0, 30.0)], store_stride=8),
 }
 
 POINT_CASES = {

@@ -100,6 +100,9 @@ def run_render_case(name, case):
                                          cull_clouds=case.get('cull_clouds'),
                                          binarize_clouds=case.get('binarize_clouds'))
     chk = float(planes.double().sum() + u_c.double().sum() + dec['w1'].double().sum())
+    st = int(case.get('store_stride', 1))          # big cases keep every st-th ray of the reference output
+    if st > 1:
+        rgb, depth, wsum, xyz = (t[:, ::st].contiguous() for t in (rgb, depth, wsum, xyz))
     np.savez_compressed(os.path.join(HERE, f'render_{name}.npz'),
                         rgb=rgb.numpy(), depth=depth.numpy(), wsum=wsum.numpy(), xyz=xyz.numpy(),
                         ro=ro.numpy() if ro.numel() <= 3 * 4096 * 2 else ro[:, ::97].numpy(),

@@ -20,7 +20,13 @@ def test_reference_arm_prints_the_contract_line():
     assert d['steps'] == 1 and d['scaling'] == 'weak' and d['vs_baseline'] is None and d['data'] == 'synthetic'
     assert 'workload' in d['config'] and '96+96' in d['config']['workload']
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
+    # kind "reference" = the unmodified reference imported from baseline/_ref (baseline/install_ref.sh), "port" = the oracle
+    have_ref = os.path.isdir(os.path.join(ROOT, 'baseline', '_ref', '_train', 'eg3dc', 'src', 'training'))
+    assert cb['kind'] == ('reference' if have_ref else 'port') and cb['cores'] >= 1 and cb['value'] == d['value'] and cb['sample']
+    # same `config` as the GPU arm prints (the driver compares them); the per-step sample is described in cpu_baseline
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d['config'] == bench.workload_config(1, 'tc_3xbf16', 'fp32') and d['warmup'] == 1
     assert d['e2e'] == {'value': d['value'], 'unit': 'views/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['gpu_launches'] == 0
 

@@ -103,3 +103,37 @@ def test_plane_reuse_memo_runs_backbone_once_per_subject():
     assert g.backbone.synthesis(ws2, big, noise_mode='const') is not d
     memo.clear()
     assert g.backbone.synthesis(ws2, cond, noise_mode='const') is not c
+
+
+def test_plane_reuse_memo_noise_mode_of_calls_that_do_not_name_one():
+    """G.f / G.synthesis never pass noise_mode (the reference's layers then draw fresh noise per call).  The memo either
+    passes an explicit 'const' on (default: deterministic sweep, cached) or, with default_noise_mode=None, leaves the call
+    alone and does not cache it - it never replays one random draw for all views."""
+    import torch
+    from panic3d_b200 import dropin
+
+    class Backbone:
+        def __init__(self):
+            self.modes = []
+
+        def synthesis(self, ws, cond, update_emas=False, noise_mode='random', **kw):
+            self.modes.append(noise_mode)
+            return ws.sum() + torch.zeros(1, 96, 4, 4) + len(self.modes)
+
+    class G:
+        pass
+    ws = torch.randn(1, 14, 512)
+    g = G(); g.backbone = Backbone()
+    bb = g.backbone
+    memo = dropin.enable_plane_reuse(g)
+    a = g.backbone.synthesis(ws, None)
+    assert g.backbone.synthesis(ws.clone(), None) is a
+    assert bb.modes == ['const'] and (memo.misses, memo.hits) == (1, 1)
+    g2 = G(); g2.backbone = Backbone()
+    bb2 = g2.backbone
+    memo2 = dropin.enable_plane_reuse(g2, default_noise_mode=None)
+    x = g2.backbone.synthesis(ws, None)
+    y = g2.backbone.synthesis(ws, None)
+    assert x is not y and bb2.modes == ['random', 'random'] and (memo2.misses, memo2.hits) == (0, 0)
+    z = g2.backbone.synthesis(ws, None, noise_mode='const')
+    assert g2.backbone.synthesis(ws, None, noise_mode='const') is z and memo2.hits == 1

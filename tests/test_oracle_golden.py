@@ -20,8 +20,9 @@ def test_render_matches_reference(name):
     assert g['case'] == json.loads(json.dumps(RENDER_CASES[name])), 'fixture is stale: rerun tests/golden/make_golden.py'
     assert abs(input_checksum(g['case']) - float(g['input_checksum'])) < 1e-6 * max(1.0, abs(float(g['input_checksum'])))
     rgb, depth, wsum, xyz = oracle_render(g['case'])
+    st = int(g['case'].get('store_stride', 1))          # big cases keep every st-th ray of the reference output
     for got, key in ((rgb, 'rgb'), (depth, 'depth'), (wsum, 'wsum'), (xyz, 'xyz')):
-        err = (got - g[key]).abs().max().item()
+        err = (got[:, ::st] - g[key]).abs().max().item()
         assert err < TOL, f'{name}:{key} max abs err {err}'
 
 

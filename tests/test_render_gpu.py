@@ -64,10 +64,17 @@ def gpu_render(case, mlp_mode=0, planes_layout='nchw'):
     return [t.cpu() for t in out], (ro.cpu(), rd.cpu())
 
 
+def _strided(case, outs):
+    """Big cases store every `store_stride`-th ray of the reference output (tests/golden/make_golden.py)."""
+    st = int(case.get('store_stride', 1))
+    return [o[:, ::st] for o in outs] if st > 1 else list(outs)
+
+
 @pytest.mark.parametrize('name', sorted(RENDER_CASES))
 def test_render_matches_reference_fixture(name):
     g = load_golden('render', name)
-    (rgb, depth, wsum, xyz), _ = gpu_render(g['case'])
+    outs, _ = gpu_render(g['case'])
+    rgb, depth, wsum, xyz = _strided(g['case'], outs)
     has_cull = bool(g['case'].get('cull_clouds') or g['case'].get('binarize_clouds'))
     for got, key in ((rgb, 'rgb'), (depth, 'depth'), (wsum, 'wsum'), (xyz, 'xyz')):
         err = (got - g[key]).abs()
@@ -195,13 +202,18 @@ def test_full_size_properties():
 # ---------------------------------------------------------------------------------------------
 # fused tcgen05 renderer (mlp_mode 1 = 3-pass split bf16 tensor cores, 2 = single-pass bf16)
 # ---------------------------------------------------------------------------------------------
-FUSED_CASES = ['config1', 'mid_train48', 'mid_eval96']
+FUSED_CASES = ['config1', 'mid_train48', 'mid_eval96', 'fused48_ortho', 'fused48_auto_limits', 'fused48_disparity',
+               'fused48_black_eg3dplanes', 'fused48_shared_planes', 'fused48_binarize', 'fused96_lrmul_black', 'headline96']
 
 
 @pytest.mark.parametrize('name', FUSED_CASES)
 def test_fused_tc_3xbf16_matches_reference_fixture(name):
+    """The benchmarked kernel (k_render_ws, mlp_mode 1) against outputs of the unmodified reference: BASELINE configs[0],
+    the option matrix (ortho rays, 'auto' limits, disparity, EG3D plane order, black background, shared planes, binarize,
+    lr_mul) at 48+48 / 96+96, and `headline96` = the benchmarked configuration itself (128^2 rays, 96+96, 512^2 planes)."""
     g = load_golden('render', name)
-    (rgb, depth, wsum, xyz), _ = gpu_render(g['case'], mlp_mode=1)
+    outs, _ = gpu_render(g['case'], mlp_mode=1)
+    rgb, depth, wsum, xyz = _strided(g['case'], outs)
     has_cull = bool(g['case'].get('cull_clouds') or g['case'].get('binarize_clouds'))
     for got, key in ((rgb, 'rgb'), (depth, 'depth'), (wsum, 'wsum'), (xyz, 'xyz')):
         err = (got - g[key]).abs()
@@ -211,6 +223,35 @@ def test_fused_tc_3xbf16_matches_reference_fixture(name):
         else:
             assert err.max().item() < TOL, f'{name}:{key} max abs err {err.max().item()}'
         print(f'{name}:{key} fused 3xbf16 max abs err {err.max().item():.3e}')
+
+
+def test_fused_headline_config_matches_live_oracle_and_is_the_default_path():
+    """BASELINE configs[1] geometry (128x128 rays, 96+96 samples, 512^2 planes; N=2) through the DEFAULT renderer settings
+    (mlp_mode 'auto' -> the fused tcgen05 kernel) against the CPU oracle run live on the box, every ray, strict tolerance."""
+    from panic3d_b200.training.volumetric_rendering.renderer import ImportanceRenderer
+    from panic3d_b200 import _lib
+    case = RENDER_CASES['headline96']
+    ref = oracle_render(case)
+    dev = _dev()
+    planes, dec, c2w, K, u_c, u_f, opts = build_case_inputs(case)
+    ro, rd = gpu_rays(case, c2w, K, dev)
+    r = ImportanceRenderer(use_triplane=True)
+    assert r.mlp_mode == 'auto'
+    r.injected_noise = (u_c, u_f)
+    _lib.lib().p3d_profile_enable(1)
+    _lib.lib().p3d_profile_read(None, None, 0, 1)
+    with torch.no_grad():
+        out = r(planes.to(dev), make_decoder(dec, dev), ro, rd, opts)
+    torch.cuda.synchronize()
+    import ctypes as C
+    ms = (C.c_double * 8)(); n = (C.c_uint64 * 8)()
+    _lib.lib().p3d_profile_read(ms, n, 8, 1)
+    _lib.lib().p3d_profile_enable(0)
+    assert n[5] == 1 and n[0] == 0, 'the default path must be the fused kernel (profile slot 5), not the SIMT kernels'
+    for got, want, key in zip(out, ref, ('rgb', 'depth', 'wsum', 'xyz')):
+        err = (got.cpu() - want).abs().max().item()
+        print(f'headline96 vs live oracle: {key} max abs err {err:.3e}')
+        assert err < TOL, (key, err)
 
 
 @pytest.mark.parametrize('name', ['config1'])
@@ -297,6 +338,88 @@ def test_renderer_backward_matches_oracle_autograd(name):
         err = (g_.cpu() - r_).abs().max().item()
         scale = max(1e-3, r_.abs().max().item())
         assert err < 2e-3 * scale, f'{name}:{nm} max abs err {err} (scale {scale})'
+
+
+@pytest.mark.parametrize('name', sorted(POINT_CASES))
+def test_run_model_backward_matches_oracle_autograd(name):
+    """ImportanceRenderer.run_model under autograd (renderer.py:266-280): gradients w.r.t. tri-planes and decoder tensors
+    for random incoming (g_rgb, g_sigma) against torch.autograd on the CPU oracle."""
+    from panic3d_b200.training.volumetric_rendering.renderer import ImportanceRenderer
+    g = load_golden('points', name)
+    case = g['case']
+    dev = _dev()
+    planes, dec, *_r, opts = build_case_inputs(case)
+    pts = g['pts']
+    rng = np.random.default_rng(case['seed'] + 7)
+    N, K = pts.shape[0], pts.shape[1]
+    gw = [torch.from_numpy(rng.standard_normal(sh).astype(np.float32)) for sh in ((N, K, 32), (N, K, 1))]
+    pl = planes.clone().requires_grad_(True)
+    dref = {k: (v.clone().requires_grad_(True) if isinstance(v, torch.Tensor) else v) for k, v in dec.items()}
+    rgb_o, sig_o = orc.run_model(pl, dref, pts, opts, case.get('use_triplane', True))
+    ref = torch.autograd.grad((rgb_o * gw[0]).sum() + (sig_o * gw[1]).sum(), [pl, dref['w1'], dref['b1'], dref['w2'], dref['b2']])
+    r = ImportanceRenderer(use_triplane=case.get('use_triplane', True))
+    d = make_decoder(dec, dev).requires_grad_(True)
+    pg = planes.to(dev).requires_grad_(True)
+    out = r.run_model(pg, d, pts.to(dev), None, opts)
+    assert out['rgb'].requires_grad and out['sigma'].requires_grad
+    assert (out['rgb'].detach().cpu() - g['rgb']).abs().max().item() < TIGHT
+    assert (out['sigma'].detach().cpu() - g['sigma']).abs().max().item() < TIGHT
+    got = torch.autograd.grad((out['rgb'] * gw[0].to(dev)).sum() + (out['sigma'] * gw[1].to(dev)).sum(),
+                              [pg, d.net[0].weight, d.net[0].bias, d.net[2].weight, d.net[2].bias])
+    for g_, r_, nm in zip(got, ref, ('planes', 'w1', 'b1', 'w2', 'b2')):
+        assert g_.shape == r_.shape, nm
+        err = (g_.cpu() - r_).abs().max().item()
+        scale = max(1e-3, r_.abs().max().item())
+        assert err < 2e-3 * scale, f'{name}:{nm} max abs err {err} (scale {scale})'
+
+
+def test_density_regularisation_graph_of_the_training_loop():
+    """The Greg phase of loss_orthocondA.py:579-600 on the renderer level: sigma of 2K points (K random + K perturbed)
+    through run_model, TV loss = l1(sigma[:K], sigma[K:]) * density_reg, backward into the tri-planes (i.e. the backbone)
+    and the decoder - against the same graph on the CPU oracle."""
+    from panic3d_b200.training.volumetric_rendering.renderer import ImportanceRenderer
+    case = POINT_CASES['pts_small']
+    dev = _dev()
+    planes, dec, *_r, opts = build_case_inputs(case)
+    gen = torch.Generator().manual_seed(5)
+    N, K = planes.shape[0], 1000
+    initial = torch.rand((N, K, 3), generator=gen) * 2 - 1
+    perturbed = initial + torch.randn((N, K, 3), generator=gen) * 0.004          # density_reg_p_dist
+    coords = torch.cat([initial, perturbed], dim=1) * (opts['box_warp'] / 2)
+
+    def tv(sigma):
+        return torch.nn.functional.l1_loss(sigma[:, :K], sigma[:, K:]) * 0.25     # density_reg
+
+    pl = planes.clone().requires_grad_(True)
+    dref = {k: (v.clone().requires_grad_(True) if isinstance(v, torch.Tensor) else v) for k, v in dec.items()}
+    _, sig_o = orc.run_model(pl, dref, coords, opts, True)
+    ref = torch.autograd.grad(tv(sig_o), [pl, dref['w1'], dref['b1'], dref['w2'], dref['b2']])
+    r = ImportanceRenderer(use_triplane=True)
+    d = make_decoder(dec, dev).requires_grad_(True)
+    pg = planes.to(dev).requires_grad_(True)
+    loss = tv(r.run_model(pg, d, coords.to(dev), torch.rand_like(coords).to(dev), opts)['sigma'])
+    assert abs(loss.item() - tv(sig_o).item()) < 1e-5
+    loss.mul(1.0).backward()
+    for g_, r_, nm in zip((pg.grad, d.net[0].weight.grad, d.net[0].bias.grad, d.net[2].weight.grad, d.net[2].bias.grad), ref,
+                          ('planes', 'w1', 'b1', 'w2', 'b2')):
+        err = (g_.cpu() - r_).abs().max().item()
+        scale = max(1e-6, r_.abs().max().item())
+        assert err < 2e-3 * scale, f'{nm} max abs err {err} (scale {scale})'
+
+
+def test_renderer_backward_is_once_differentiable():
+    from panic3d_b200.training.volumetric_rendering.renderer import ImportanceRenderer
+    case = RENDER_CASES['small_plain']
+    dev = _dev()
+    planes, dec, c2w, K, u_c, u_f, opts = build_case_inputs(case)
+    ro, rd = gpu_rays(case, c2w, K, dev)
+    r = ImportanceRenderer(use_triplane=True)
+    r.injected_noise = (u_c, u_f)
+    pg = planes.to(dev).requires_grad_(True)
+    out = r(pg, make_decoder(dec, dev), ro, rd, opts)
+    (gp,) = torch.autograd.grad(out[0].sum(), [pg], create_graph=True)
+    with pytest.raises(RuntimeError):
+        gp.sum().backward()
 
 
 def test_renderer_no_grad_path_unchanged_and_grad_path_equal():
