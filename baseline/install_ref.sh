@@ -21,3 +21,6 @@ done
 find "$DST" -name '__pycache__' -type d -prune -exec rm -rf {} +
 ( cd "$SRC" && find _train _databacks _util _scripts -type f -name '*.py' -o -name '*.cu' -o -name '*.cpp' -o -name '*.h' | sort | xargs sha1sum ) > "$DST/MANIFEST.sha1"
 echo "installed $(find "$DST" -type f | wc -l) files ($(du -sh "$DST" | cut -f1)) into $DST"
+# pre-build the reference's CUDA plugins for sm_100 (cross-compiles without a GPU); bench_config3.py / bench_ops.py point
+# TORCH_EXTENSIONS_DIR at this directory on the GPU box
+python "$HERE/prebuild_ref_plugins.py" "$DST" "$DST/_torch_ext" 2>&1 | grep -v "No CUDA runtime" || true

@@ -1,0 +1,194 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[2]: the eval script's view sweep (`_scripts/eval/generate.py:108-130`: 4 orthographic + 12
+perspective views of one subject through `G.f`, super-resolution head on) on a synthetic-weight TriPlaneGenerator built
+with the training configuration's kwargs (`_train/eg3dc/trainers/train_eclustrousC.py:339-343,409-440,479-480`) and the eval
+loader's settings (`_train/eg3dc/util/eg3dc_v0.py:24-56`: 96+96 samples, force_sigmoid; `generate.py:53-57`: crop 0.1,
+cull 0.5; `paste_params=None` - kornia is not in this image).
+
+Two arms, one process each (module identity is decided at import time), same weights (same seed, same construction order):
+
+    python bench_config3.py --arm reference --out gpurun_out/c3_ref.pt   the UNMODIFIED reference from baseline/_ref on its own GPU
+                                                                         path: eager PyTorch renderer + its JIT CUDA plugins
+    python bench_config3.py --arm ours      --out gpurun_out/c3_ours.pt  the same reference TriPlaneGenerator / backbone / SR code
+                                                                         with panic3d_b200.dropin.install(): our renderer, ray
+                                                                         sampler and the three ops underneath it
+    python bench_config3.py --compare gpurun_out/c3_ref.pt gpurun_out/c3_ours.pt
+
+Parity pass (deterministic): backbone noise_mode='const', SR noise per the config ('none'), the renderer's jitter injected
+identically into both arms (patched torch.rand_like / torch.rand for the reference, `injected_noise` for ours).
+Timing pass: the sweep as the eval script runs it (random noise, own jitter), CUDA events around each G.f call."""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+REF_TREE = os.path.join(ROOT, 'baseline', '_ref')
+
+
+def sweep_views():
+    """generate.py:108-117: camO front/left/right/back (fov -1 = orthographic) + camP cam60[spin12] (fov 30)."""
+    import _databacks.lustrous_renders_v1 as dk
+    views = [('camO', 0.0, 0.0, -1.0), ('camO', 0.0, 90.0, -1.0), ('camO', 0.0, -90.0, -1.0), ('camO', 0.0, 180.0, -1.0)]
+    for v in dk.camsubs['spin12']:
+        e, a = dk.cam60[v]
+        views.append(('camP', float(e), float(a), 30.0))
+    return views
+
+
+class InjectRand:
+    """Feed pre-drawn uniforms to the reference renderer's torch.rand_like / torch.rand calls, in call order."""
+
+    def __init__(self, torch, queue):
+        self.torch, self.queue = torch, list(queue)
+
+    def __enter__(self):
+        t = self.torch
+        self._rl, self._r = t.rand_like, t.rand
+        q = self.queue
+
+        def rand_like(x, *a, **k):
+            u = q.pop(0)
+            assert u.shape == x.shape, (u.shape, x.shape)
+            return u.to(x.device).clone()
+
+        def rand(*size, **k):
+            u = q.pop(0)
+            return u.to(k.get('device', u.device)).clone()
+        t.rand_like, t.rand = rand_like, rand
+        return self
+
+    def __exit__(self, *exc):
+        self.torch.rand_like, self.torch.rand = self._rl, self._r
+
+
+def build_generator(args, torch):
+    import training.triplane as tp
+    res, R = (64, 16) if args.tiny else (512, 128)
+    rk = dict(image_resolution=res, disparity_space_sampling=False, clamp_mode='softplus',
+              superresolution_module='training.superresolution.SuperresolutionHybrid8XDC', c_gen_conditioning_zero=True,
+              gpc_reg_prob=None, c_scale=1.0, superresolution_noise_mode='none', density_reg=0.25, density_reg_p_dist=0.004,
+              reg_type='l1', decoder_lr_mul=1.0, sr_antialias=True, white_back=True, triplane_depth=1, use_triplane=True,
+              tanh_rgb_output=False, box_warp=0.7, ray_start=0.5, ray_end=1.5, depth_resolution=96, depth_resolution_importance=96,
+              avg_camera_radius=1.0, avg_camera_pivot=[0, 0, 0])
+    cb, cm = (2048, 32) if args.tiny else (32768, 512)
+    torch.manual_seed(0)
+    G = tp.TriPlaneGenerator(z_dim=512, c_dim=25, w_dim=512, img_resolution=512, img_channels=3, rendering_kwargs=rk,
+                             cond_mode='none', mapping_kwargs=dict(num_layers=2), channel_base=cb, channel_max=cm,
+                             fused_modconv_default='inference_only', num_fp16_res=0, sr_num_fp16_res=4,
+                             sr_kwargs=dict(channel_base=cb, channel_max=cm, fused_modconv_default='inference_only'),
+                             triplane_width=32, backbone_resolution=args.plane)
+    G = G.eval().requires_grad_(False)
+    G.neural_rendering_resolution = R
+    G.set_force_sigmoid(True)                                  # load_eg3dc_model(force_sigmoid=True), generate.py:54
+    return G, R
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--arm', choices=['reference', 'ours'])
+    ap.add_argument('--out')
+    ap.add_argument('--compare', nargs=2)
+    ap.add_argument('--plane', type=int, default=256, help='backbone_resolution (256 in the shipped model; BASELINE synthetic: 512)')
+    ap.add_argument('--tiny', action='store_true', help='small channels / 16x16 rays (CPU smoke test of the harness)')
+    ap.add_argument('--device', default='cuda:0')
+    ap.add_argument('--reps', type=int, default=2, help='timed repetitions of the 16-view sweep')
+    args = ap.parse_args()
+    import torch
+    if args.compare:
+        a, b = (torch.load(f) for f in args.compare)
+        rep = {'arms': [a['arm'], b['arm']], 'views': len(a['views'])}
+        for key in ('image_raw', 'image', 'image_depth', 'image_weights', 'feature_image'):
+            if key in a and key in b:
+                d = (a[key].float() - b[key].float()).abs()
+                rep[key] = {'max_abs': float(d.max()), 'mean_abs': float(d.mean()), 'shape': list(d.shape)}
+        rep['views_per_s'] = {a['arm']: a['views_per_s'], b['arm']: b['views_per_s']}
+        rep['speedup'] = b['views_per_s'] / a['views_per_s'] if a['arm'] == 'reference' else a['views_per_s'] / b['views_per_s']
+        print(json.dumps(rep))
+        return
+    if not os.path.isdir(os.path.join(REF_TREE, '_train', 'eg3dc', 'src', 'training')):
+        raise SystemExit('baseline/_ref is missing: run `bash baseline/install_ref.sh` in the build container')
+    os.environ['PROJECT_DN'] = REF_TREE
+    os.environ.setdefault('TORCH_EXTENSIONS_DIR', os.path.join(REF_TREE, '_torch_ext'))
+    sys.path[:0] = [ROOT, REF_TREE, os.path.join(REF_TREE, '_train', 'eg3dc', 'src')]
+    sys.modules.setdefault('kornia', types.ModuleType('kornia'))
+    dev = torch.device(args.device)
+    if args.arm == 'ours':
+        import panic3d_b200.dropin as dropin
+        installed = dropin.install()
+    import training.triplane as tp
+    mod_file = sys.modules[tp.ImportanceRenderer.__module__].__file__
+    assert ('baseline/_ref' in mod_file.replace(os.sep, '/')) == (args.arm == 'reference'), mod_file
+    G, R = build_generator(args, torch)
+    G = G.to(dev)
+    views = sweep_views()
+    ws = None
+    S = int(G.rendering_kwargs['depth_resolution'])
+    Sf = int(G.rendering_kwargs['depth_resolution_importance'])
+
+    def xin_for(elev, azim, fov):
+        one = torch.ones(1, device=dev)
+        x = {'elevations': elev * one, 'azimuths': azim * one, 'fovs': fov * one, 'cond': {}, 'seeds': [0],
+             'triplane_crop': 0.1, 'cull_clouds': 0.5}
+        if ws is not None:
+            x['ws'] = ws
+        return x
+
+    outs = {k: [] for k in ('image_raw', 'image', 'image_depth', 'image_weights')}
+    syn_fwd = G.backbone.synthesis.forward                      # an nn.Module: patch its forward on the instance
+    with torch.no_grad():
+        # ---- parity pass
+        G.backbone.synthesis.forward = lambda *a, **k: syn_fwd(*a, **dict(k, noise_mode='const'))
+        gen = torch.Generator().manual_seed(123)
+        for i, (_cm, e, a, f) in enumerate(views):
+            u_c = torch.rand(1, R * R, S, 1, generator=gen)
+            u_f = torch.rand(R * R, Sf, generator=gen)
+            x = xin_for(e, a, f)
+            if args.arm == 'reference':
+                with InjectRand(torch, [u_c, u_f]):
+                    out = G.f(x)
+            else:
+                G.renderer.injected_noise = (u_c, u_f)
+                out = G.f(x)
+                G.renderer.injected_noise = None
+            ws = x['ws']
+            for k in outs:
+                outs[k].append(out[k].float().cpu())
+        G.backbone.synthesis.forward = syn_fwd
+        # ---- timing pass: the sweep as generate.py runs it
+        if dev.type == 'cuda':
+            for (_cm, e, a, f) in views[:3]:
+                G.f(xin_for(e, a, f))
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(args.reps):
+                for (_cm, e, a, f) in views:
+                    G.f(xin_for(e, a, f))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        else:
+            t0 = time.perf_counter()
+            for (_cm, e, a, f) in views[:2]:
+                G.f(xin_for(e, a, f))
+            dt = (time.perf_counter() - t0) * len(views) / 2 * args.reps
+    vps = args.reps * len(views) / dt
+    res = {k: torch.cat(v) for k, v in outs.items()}
+    res.update(arm=args.arm, views=views, views_per_s=vps, plane=args.plane)
+    if args.out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+        torch.save(res, args.out)
+    line = {'config': 'BASELINE configs[2]: G.f 16-view sweep, SR on, synthetic weights', 'arm': args.arm, 'views_per_s': vps,
+            'ms_per_view': 1e3 / vps, 'plane': args.plane, 'rays': R * R, 'samples': [S, Sf],
+            'renderer_module': mod_file.replace(ROOT, '.'), 'image_mean': float(res['image'].mean())}
+    if args.arm == 'ours':
+        from panic3d_b200 import _lib
+        line['gpu_launches'] = _lib.launch_count()
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

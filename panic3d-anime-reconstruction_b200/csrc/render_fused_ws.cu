@@ -40,7 +40,7 @@ constexpr int kColD1 = 0, kColSig = 64, kColD2 = 96;   // D2[slot][tile6] = 96 +
 #define P3D_WS_G256 0          // 1: gather with 256-bit loads, 4 lanes per row (measured slower: each half of an LDG.256 is its own L1 wavefront per line)
 #endif
 #ifndef P3D_WS_LBO_A1
-#define P3D_WS_LBO_A1 2048     // byte distance between the K-chunks of the A1 tile (2080 staggers them over the banks)
+#define P3D_WS_LBO_A1 2080     // byte distance between the K-chunks of the A1 tile: 2048 + 32 staggers them over the banks (conflict-free stores)
 #endif
 #ifndef P3D_WS_POS16
 #define P3D_WS_POS16 1

@@ -43,7 +43,8 @@ constexpr int kTmemColsWS = 512;
 constexpr int kColD1 = 0, kColSig = 64, kColCA = 96, kColFA = 384;   // see the TMEM map above
 __device__ __forceinline__ uint32_t d2_col(int n, int pass, int k) { return (uint32_t)(pass == 0 ? kColCA + (n % 3) * 96 + k * 32 : kColFA + k * 32); }
 
-constexpr int kSBO = 128, kLBO_A = 2048, kLBO_W1 = 1024, kLBO_W2C = 512, kLBO_W2S = 256;
+constexpr int kSBO = 128, kLBO_A = 2048, kLBO_A1 = 2080, kLBO_W1 = 1024, kLBO_W2C = 512, kLBO_W2S = 256;
+constexpr bool kG256 = false;
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
 struct GroupState {                               // written by G (t_c, crop), E (sg_*), R (t_f)
@@ -52,17 +53,17 @@ struct GroupState {                               // written by G (t_c, crop), E
 };
 struct SlotState {                                // written by R (composite), read by E (colours)
     float om[2 * kRowsG];                         // omega per merged position, [ray][2S]
-    int pos[2 * kRowsG];                          // merged position of coarse rows [0,384) and fine rows [384,768)
+    unsigned short pos[2 * kRowsG];                          // merged position of coarse rows [0,384) and fine rows [384,768)
     float acc[8][kRgb];
     float back[8];
 };
 
 struct __align__(1024) WsSmem {
-    unsigned char a1[kNA][2][8192];
+    unsigned char a1[kNA][2][4 * kLBO_A1];
     unsigned char a2[2][2][16384];
     unsigned char w1[2][4096], w2c[2][4096], w2s[2][2048];
     float b1[kHidden], b2c[kRgb], b2s, pad0[3];
-    int2 taps[kGW][16][12];                       // 16 rows at a time per gather warp
+    uint4 tab[kGW][32][4];                        // tap table of a gather warp's 32 rows (see "gather" below)
     GroupState st[kStates];
     SlotState slot[2];
     float rscratch[kRW][768];                      // private scratch of each ray warp (importance / merge)
@@ -170,38 +171,84 @@ __device__ __forceinline__ void split1(float x, unsigned short& hi, unsigned sho
 }
 __device__ __forceinline__ int tile_off(int row, int k, int lbo) { return (row >> 3) * kSBO + (k >> 3) * lbo + (row & 7) * 16 + (k & 7) * 2; }
 
-__device__ __forceinline__ void plane_taps32(const Geom& g, const WsArgs& a, int pbase, float ca, float cb, int2* out) {
+// ------------------------------------------------------------------------------------------ gather
+// Tap table: one 64 B record per row - chunk 0 = {o[0], o[1], o[2], flags}, chunk 1+p = the four bilinear weights of plane p
+// (w00, w01, w10, w11; rows y, y+1 x columns x, x+1) - chunk c of row r stored at position c ^ ((r >> 1) & 3), which makes
+// both the lane = row writes and the 8-rows-per-phase reads of the gather conflict-free.  o[p] is the element offset of texel
+// (ya, xa) of plane p inside the view's tri-plane, with (ya, xa) CLAMPED to [0, H-2] x [0, W-2]: the 2 x 2 footprint that is
+// loaded is always inside the plane, and the weights are moved onto the loaded texels (grid_sample's zero padding,
+// renderer.py:68-81: a tap outside the plane contributes nothing, so its weight is dropped; a footprint that hangs over the
+// edge by one texel keeps the weights of its inside texels).  flags bit p = plane p has a non-zero weight; the loads of a
+// plane whose bit is clear are predicated off (its registers keep older, finite texel values that meet weights of 0).
+__device__ __forceinline__ uint32_t tab_off(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
+
+__device__ __forceinline__ bool plane_taps_rec(const Geom& g, const WsArgs& a, int pbase, float ca, float cb, uint32_t& o, float4& w) {
     const float gx = __fmul_rn(ca, g.coord_scale), gy = __fmul_rn(cb, g.coord_scale);
     const float fx = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)g.W), 1.f), 0.5f);
     const float fy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)g.H), 1.f), 0.5f);
-    const bool sane = (fx > -2.f) && (fx < (float)g.W + 1.f) && (fy > -2.f) && (fy < (float)g.H + 1.f);
+    const bool sane = (fx > -2.f) && (fx < (float)g.W + 1.f) && (fy > -2.f) && (fy < (float)g.H + 1.f);   // false for NaN too
     const float x0f = floorf(fx), y0f = floorf(fy);
     const float wx1 = fx - x0f, wy1 = fy - y0f;
     const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
     const int x0 = sane ? (int)x0f : -4, y0 = sane ? (int)y0f : -4;
-    const bool vx0 = (unsigned)x0 < (unsigned)g.W, vx1 = (unsigned)(x0 + 1) < (unsigned)g.W;
-    const bool vy0 = (unsigned)y0 < (unsigned)g.H, vy1 = (unsigned)(y0 + 1) < (unsigned)g.H;
-    const int o00 = pbase + y0 * a.srow + x0 * a.scol;
-    int4 lo, hi;
-    lo.x = (vx0 && vy0) ? o00 : 0;                     lo.y = __float_as_int((vx0 && vy0) ? wx0 * wy0 : 0.f);
-    lo.z = (vx1 && vy0) ? o00 + a.scol : 0;            lo.w = __float_as_int((vx1 && vy0) ? wx1 * wy0 : 0.f);
-    hi.x = (vx0 && vy1) ? o00 + a.srow : 0;            hi.y = __float_as_int((vx0 && vy1) ? wx0 * wy1 : 0.f);
-    hi.z = (vx1 && vy1) ? o00 + a.srow + a.scol : 0;   hi.w = __float_as_int((vx1 && vy1) ? wx1 * wy1 : 0.f);
-    reinterpret_cast<int4*>(out)[0] = lo;
-    reinterpret_cast<int4*>(out)[1] = hi;
+    const int xa = min(max(x0, 0), g.W - 2), ya = min(max(y0, 0), g.H - 2);
+    const int dx = x0 - xa, dy = y0 - ya;                     // 0 inside, -1 / +1: the footprint hangs over the low / high edge
+    const float wl = dx == 0 ? wx0 : (dx == -1 ? wx1 : 0.f), wr = dx == 0 ? wx1 : (dx == 1 ? wx0 : 0.f);
+    const float wt = dy == 0 ? wy0 : (dy == -1 ? wy1 : 0.f), wb = dy == 0 ? wy1 : (dy == 1 ? wy0 : 0.f);
+    o = (uint32_t)(pbase + ya * a.srow + xa * a.scol);
+    w = make_float4(wl * wt, wr * wt, wl * wb, wr * wb);
+    return ((unsigned)(dx + 1) < 3u) && ((unsigned)(dy + 1) < 3u);
 }
-template <bool BF16>
-__device__ __forceinline__ float4 load_quad32(const void* qbase, int off) {
-    float4 r;
+// eight consecutive channels of one texel (32 B fp32 / 16 B bf16) at addr + IMM bytes, predicated; v keeps its old value when !pred
+template <bool BF16, int IMM>
+__device__ __forceinline__ void load_oct(float (&v)[8], const char* addr, bool pred) {
     if (BF16) {
-        unsigned int lo, hi;
-        asm("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %3, 2, %2;\n\tld.global.nc.v2.u32 {%0,%1}, [a];\n\t}" : "=r"(lo), "=r"(hi) : "l"(qbase), "r"(off));
-        r = make_float4(__uint_as_float(lo << 16), __uint_as_float(lo & 0xffff0000u), __uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u));
+        uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4+%6];\n\t}"
+                     : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3) : "l"(addr), "r"((int)pred), "n"(IMM));
+        if (pred) {
+            v[0] = __uint_as_float(r0 << 16); v[1] = __uint_as_float(r0 & 0xffff0000u); v[2] = __uint_as_float(r1 << 16); v[3] = __uint_as_float(r1 & 0xffff0000u);
+            v[4] = __uint_as_float(r2 << 16); v[5] = __uint_as_float(r2 & 0xffff0000u); v[6] = __uint_as_float(r3 << 16); v[7] = __uint_as_float(r3 & 0xffff0000u);
+        }
     } else {
-        asm("{\n\t.reg .u64 a;\n\tmad.wide.s32 a, %5, 4, %4;\n\tld.global.nc.v4.f32 {%0,%1,%2,%3}, [a];\n\t}"
-            : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(qbase), "r"(off));
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %9, 0;\n\t@p ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+%10];\n\t}"
+                     : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])
+                     : "l"(addr), "r"((int)pred), "n"(IMM));
     }
-    return r;
+}
+// four consecutive channels of one texel (16 B fp32 / 8 B bf16) at addr + IMM bytes, predicated; v keeps its old value when !pred
+template <bool BF16, int IMM>
+__device__ __forceinline__ void load_quad_p(float (&v)[4], const char* addr, bool pred) {
+    if (BF16) {
+        uint32_t r0 = 0, r1 = 0;
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p ld.global.nc.v2.u32 {%0,%1}, [%2+%4];\n\t}"
+                     : "+r"(r0), "+r"(r1) : "l"(addr), "r"((int)pred), "n"(IMM));
+        if (pred) { v[0] = __uint_as_float(r0 << 16); v[1] = __uint_as_float(r0 & 0xffff0000u); v[2] = __uint_as_float(r1 << 16); v[3] = __uint_as_float(r1 & 0xffff0000u); }
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4+%6];\n\t}"
+                     : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) : "l"(addr), "r"((int)pred), "n"(IMM));
+    }
+}
+__device__ __forceinline__ void fma4(unsigned long long (&acc)[2], const float (&v)[4], float w) {
+    unsigned long long ww;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        unsigned long long vv;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "f"(v[2 * j]), "f"(v[2 * j + 1]));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j]) : "l"(vv), "l"(ww));
+    }
+}
+// acc[0..8) += v[0..8) * w as four packed FFMA2 (the scalar weight is broadcast by the instruction)
+__device__ __forceinline__ void fma8(unsigned long long (&acc)[4], const float (&v)[8], float w) {
+    unsigned long long ww;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        unsigned long long vv;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "f"(v[2 * j]), "f"(v[2 * j + 1]));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j]) : "l"(vv), "l"(ww));
+    }
 }
 
 // pass j of a CTA with N groups:  C(0) C(1) | F(0) C(2) | F(1) C(3) | ... | F(N-2) F(N-1)   (N == 1: C(0) F(0))
@@ -222,15 +269,16 @@ __device__ __forceinline__ TileDesc tile_at(int q, int N) {
 }
 
 // ------------------------------------------------------------------------------------------
-template <bool BF16, int S>
+template <bool BF16, int S, int SCOL>
 __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
     constexpr int Sf = S, L = 2 * S;
     constexpr int RPT = S / 3;                   // rows per ray per tile (32 or 16)
     constexpr int GR = 128 / RPT;                // rays per group (4 or 8)
     extern __shared__ unsigned char smem_raw[];
-    WsSmem& sm = *reinterpret_cast<WsSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));   // keeps the shared address space
     const Geom& g = a.g;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);      // provably warp-uniform
     const int n_my = (a.n_groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // groups of this CTA
     const int T = 6 * n_my;
 
@@ -253,7 +301,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
     for (int i = tid; i < kHidden * kC; i += kThreadsWS) {            // W1' = W1 * gain * log2(e)   (64 x 32)
         const int n = i / kC, k = i % kC;
         unsigned short hi, lo;
-        split1(__fmul_rn(a.w1[i], g.w1_gain) * kLog2e, hi, lo);
+        split1(__fmul_rn(a.w1[i], g.w1_gain) * (kLog2e / 3.f), hi, lo);      // the 1/3 is the plane mean
         const int off = tile_off(n, k, kLBO_W1);
         *reinterpret_cast<unsigned short*>(sm.w1[0] + off) = hi;
         *reinterpret_cast<unsigned short*>(sm.w1[1] + off) = lo;
@@ -287,6 +335,16 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
         // =========================================================================== GATHER
         const int gw = warp, team = gw >> 2, wt = gw & 3;
         Tick tk_(a.timing, blockIdx.x == 0 && gw == 0 && lane == 0);
+        constexpr int kEsz = BF16 ? 2 : 4;
+        constexpr int kImmX = SCOL * kEsz;                                  // byte offset of the x+1 texel when the column stride is static
+        const long long scolB = (long long)a.scol * kEsz, srowB = (long long)a.srow * kEsz;
+        unsigned char* tab = reinterpret_cast<unsigned char*>(sm.tab[gw]);
+        const int q8 = lane >> 3, rr = lane & 7;                            // gather lane = (channel octet q8, row rr of the round)
+        float v[6][8];
+#pragma unroll
+        for (int k = 0; k < 6; ++k)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) v[k][c] = 0.f;
         int it = 0;
         for (int q = 0; q < T; ++q) {
             const TileDesc td = tile_at(q, n_my);
@@ -299,109 +357,153 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             if (td.pass == 0) mbar_wait(&sm.state_free[td.n & 3], ((td.n >> 2) & 1) ^ 1);
             else mbar_wait(&sm.fine_ready[td.n & 3], (td.n >> 2) & 1);
             tk_.lap(1);                                                   // [1] wait state_free / fine_ready
+            const int view = (int)(ray0 / g.M);
+            // ---- tap table of this warp's 32 rows: lane = row
+            {
+                const int trow = wt * 32 + lane;
+                const int rl = trow / RPT, s = td.k * RPT + (trow - rl * RPT);
+                const int srow = rl * S + s;                               // row in the per-group state arrays
+                const long long ray = ray0 + rl;
+                const bool live = ray < a.R;
+                float tval;
+                if (td.pass == 0) {
+                    float u = 0.f;
+                    if (live) {
+                        const long long gidx = ray * S + s;
+                        u = a.u_c ? a.u_c[gidx] : philox_uniform(g.seed, (uint64_t)gidx, 0u);
+                    }
+                    float t0 = 0.f, t1 = 0.f;
+                    if (g.ray_mode == P3D_RAYS_AUTOBOX && live) {
+                        t0 = a.ray_t0[ray]; t1 = a.ray_t1[ray];
+                        if (!(t1 > t0) && a.bounds[4]) { t0 = ordered_to_float(a.bounds[2]); t1 = ordered_to_float(a.bounds[3]); }
+                    }
+                    tval = coarse_depth(g, s, u, t0, t1);
+                    st.t_c[srow] = tval;
+                } else {
+                    tval = st.t_f[srow];
+                }
+                float px = 1e30f, py = 1e30f, pz = 1e30f;
+                if (live) {
+                    const float* o = a.ro + ray * 3;
+                    const float* d = a.rd + ray * 3;
+                    px = __fadd_rn(o[0], __fmul_rn(tval, d[0]));
+                    py = __fadd_rn(o[1], __fmul_rn(tval, d[1]));
+                    pz = __fadd_rn(o[2], __fmul_rn(tval, d[2]));
+                }
+                const bool pm = g.plane_mode == P3D_PLANES_PANIC3D;
+                uint32_t o0, o1, o2;
+                float4 w0, w1, w2;
+                const bool f0 = plane_taps_rec(g, a, 0, px, py, o0, w0);
+                const bool f1 = plane_taps_rec(g, a, a.splane, px, pz, o1, w1);
+                const bool f2 = plane_taps_rec(g, a, 2 * a.splane, pm ? py : pz, pm ? pz : px, o2, w2);
+                *reinterpret_cast<uint4*>(tab + tab_off(lane, 0)) = make_uint4(o0, o1, o2, (f0 ? 1u : 0u) | (f1 ? 2u : 0u) | (f2 ? 4u : 0u));
+                *reinterpret_cast<float4*>(tab + tab_off(lane, 1)) = w0;
+                *reinterpret_cast<float4*>(tab + tab_off(lane, 2)) = w1;
+                *reinterpret_cast<float4*>(tab + tab_off(lane, 3)) = w2;
+                st.crop[td.pass][srow] = (g.crop_on && !((fabsf(px) <= g.crop_limit) && (fabsf(pz) <= g.crop_limit))) ? 1 : 0;
+            }
+            __syncwarp();
             const int stage = my_it % kNA;
             mbar_wait(&sm.a1_empty[stage], ((my_it / kNA) & 1) ^ 1);
-            tk_.lap(2);                                                   // [2] wait a1_empty
-            const int view = (int)(ray0 / g.M);
-            const void* vplanes = BF16 ? (const void*)(reinterpret_cast<const __nv_bfloat16*>(a.planes) + (long long)view * g.stride_view)
-                                       : (const void*)(reinterpret_cast<const float*>(a.planes) + (long long)view * g.stride_view);
-            int2(*taps)[12] = sm.taps[gw];
-            const int sub = lane >> 3, qd = lane & 7;
-            const void* qplanes = BF16 ? (const void*)(reinterpret_cast<const __nv_bfloat16*>(vplanes) + 4 * qd)
-                                       : (const void*)(reinterpret_cast<const float*>(vplanes) + 4 * qd);
+            tk_.lap(2);                                                   // [2] taps + wait a1_empty
             unsigned char* a1h = sm.a1[stage][0];
             unsigned char* a1l = sm.a1[stage][1];
+            if constexpr (!kG256) {
+                // ---- gather: 8 rounds of 4 rows; lane (sub, qd) loads channels [4 qd, 4 qd + 4) of the 12 taps of row 4 round + sub:
+                //      twelve 128-bit loads in flight per lane, each warp-wide load covers four whole 128 B texels (one L1
+                //      wavefront per texel)
+                const int sub = lane >> 3, qd = lane & 7;
+                const char* vq4 = reinterpret_cast<const char*>(a.planes) + ((long long)view * g.stride_view + 4 * qd) * kEsz;
+                constexpr int kImmX4 = SCOL * kEsz;
+                float (*v4)[4] = reinterpret_cast<float (*)[4]>(&v[0][0]);           // the same 48 registers, as 12 x 4
 #pragma unroll 1
-            for (int half_tile = 0; half_tile < 2; ++half_tile) {
-                const int row0 = wt * 32 + half_tile * 16;                 // this warp's 16 rows of the tile
-                // ---- taps: lane pair per row
-                {
-                    const int lrow = lane >> 1, half = lane & 1;
-                    const int trow = row0 + lrow;
-                    const int rl = trow / RPT, s = td.k * RPT + (trow - rl * RPT);
-                    const int srow = rl * S + s;                           // row in the per-group state arrays
-                    const long long ray = ray0 + rl;
-                    const bool live = ray < a.R;
-                    float tval;
-                    if (td.pass == 0) {
-                        float u = 0.f;
-                        if (half == 0 && live) {
-                            const long long gidx = ray * S + s;
-                            u = a.u_c ? a.u_c[gidx] : philox_uniform(g.seed, (uint64_t)gidx, 0u);
-                        }
-                        u = __shfl_sync(0xffffffffu, u, lane & ~1);
-                        float t0 = 0.f, t1 = 0.f;
-                        if (g.ray_mode == P3D_RAYS_AUTOBOX && live) {
-                            t0 = a.ray_t0[ray]; t1 = a.ray_t1[ray];
-                            if (!(t1 > t0) && a.bounds[4]) { t0 = ordered_to_float(a.bounds[2]); t1 = ordered_to_float(a.bounds[3]); }
-                        }
-                        tval = coarse_depth(g, s, u, t0, t1);
-                    } else {
-                        tval = st.t_f[srow];
-                    }
-                    float px = 1e30f, py = 1e30f, pz = 1e30f;
-                    if (live) {
-                        const float* o = a.ro + ray * 3;
-                        const float* d = a.rd + ray * 3;
-                        px = __fadd_rn(o[0], __fmul_rn(tval, d[0]));
-                        py = __fadd_rn(o[1], __fmul_rn(tval, d[1]));
-                        pz = __fadd_rn(o[2], __fmul_rn(tval, d[2]));
-                    }
-                    if (half == 0) {
-                        plane_taps32(g, a, 0, px, py, taps[lrow]);
-                        plane_taps32(g, a, a.splane, px, pz, taps[lrow] + 4);
-                    } else {
-                        const bool pm = g.plane_mode == P3D_PLANES_PANIC3D;
-                        plane_taps32(g, a, 2 * a.splane, pm ? py : pz, pm ? pz : px, taps[lrow] + 8);
-                        if (td.pass == 0) st.t_c[srow] = tval;
-                        st.crop[td.pass][srow] = (g.crop_on && !((fabsf(px) <= g.crop_limit) && (fabsf(pz) <= g.crop_limit))) ? 1 : 0;
-                    }
-                }
-                __syncwarp();
-                // ---- gather: 4 rows per round, 8 lanes per row
-#pragma unroll 1
-                for (int round = 0; round < 4; ++round) {
+                for (int round = 0; round < 8; ++round) {
                     const int lrow = round * 4 + sub;
-                    const int4* tp = reinterpret_cast<const int4*>(taps[lrow]);
-                    int4 tk[6];
+                    const uint4 c0 = *reinterpret_cast<const uint4*>(tab + tab_off(lrow, 0));
+                    const bool p0 = c0.w & 1u, p1 = c0.w & 2u, p2 = c0.w & 4u;
+                    const char* b0 = vq4 + (unsigned long long)c0.x * kEsz;
+                    const char* b1 = vq4 + (unsigned long long)c0.y * kEsz;
+                    const char* b2 = vq4 + (unsigned long long)c0.z * kEsz;
+#define P3D_LD4(k, base, pr)                                                                                         \
+                    load_quad_p<BF16, 0>(v4[k], base, pr);                                                            \
+                    if (SCOL) load_quad_p<BF16, kImmX4>(v4[k + 1], base, pr); else load_quad_p<BF16, 0>(v4[k + 1], base + scolB, pr); \
+                    load_quad_p<BF16, 0>(v4[k + 2], base + srowB, pr);                                                \
+                    if (SCOL) load_quad_p<BF16, kImmX4>(v4[k + 3], base + srowB, pr); else load_quad_p<BF16, 0>(v4[k + 3], base + srowB + scolB, pr);
+                    P3D_LD4(0, b0, p0)
+                    P3D_LD4(4, b1, p1)
+                    P3D_LD4(8, b2, p2)
+#undef P3D_LD4
+                    const float4 w0 = *reinterpret_cast<const float4*>(tab + tab_off(lrow, 1));
+                    const float4 w1 = *reinterpret_cast<const float4*>(tab + tab_off(lrow, 2));
+                    const float4 w2 = *reinterpret_cast<const float4*>(tab + tab_off(lrow, 3));
+                    unsigned long long acc[2] = {0ull, 0ull};
+                    fma4(acc, v4[0], w0.x); fma4(acc, v4[1], w0.y); fma4(acc, v4[2], w0.z); fma4(acc, v4[3], w0.w);
+                    fma4(acc, v4[4], w1.x); fma4(acc, v4[5], w1.y); fma4(acc, v4[6], w1.z); fma4(acc, v4[7], w1.w);
+                    fma4(acc, v4[8], w2.x); fma4(acc, v4[9], w2.y); fma4(acc, v4[10], w2.z); fma4(acc, v4[11], w2.w);
+                    uint32_t h[2], l[2];
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) tk[k] = tp[k];
-                    float4 v[12];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) {
-                        v[2 * k] = load_quad32<BF16>(qplanes, tk[k].x);
-                        v[2 * k + 1] = load_quad32<BF16>(qplanes, tk[k].z);
+                    for (int j = 0; j < 2; ++j) {
+                        float e0, e1;
+                        asm("mov.b64 {%0, %1}, %2;" : "=f"(e0), "=f"(e1) : "l"(acc[j]));
+                        split2(e0, e1, h[j], l[j]);
                     }
-                    float4 f[3];
-#pragma unroll
-                    for (int p = 0; p < 3; ++p) {
-                        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const int4 t2 = tk[2 * p + k];
-                            const float wa = __int_as_float(t2.y), wb = __int_as_float(t2.w);
-                            const float4 va = v[4 * p + 2 * k], vb = v[4 * p + 2 * k + 1];
-                            acc.x = fmaf(va.x, wa, acc.x); acc.y = fmaf(va.y, wa, acc.y); acc.z = fmaf(va.z, wa, acc.z); acc.w = fmaf(va.w, wa, acc.w);
-                            acc.x = fmaf(vb.x, wb, acc.x); acc.y = fmaf(vb.y, wb, acc.y); acc.z = fmaf(vb.z, wb, acc.z); acc.w = fmaf(vb.w, wb, acc.w);
-                        }
-                        f[p] = acc;
-                    }
-                    const float third = 1.f / 3.f;
-                    const float fx = ((f[0].x + f[1].x) + f[2].x) * third, fy = ((f[0].y + f[1].y) + f[2].y) * third;
-                    const float fz = ((f[0].z + f[1].z) + f[2].z) * third, fw = ((f[0].w + f[1].w) + f[2].w) * third;
-                    uint32_t h01, l01, h23, l23;
-                    split2(fx, fy, h01, l01);
-                    split2(fz, fw, h23, l23);
-                    const int off = tile_off(row0 + lrow, 4 * qd, kLBO_A);
-                    *reinterpret_cast<uint2*>(a1h + off) = make_uint2(h01, h23);
-                    *reinterpret_cast<uint2*>(a1l + off) = make_uint2(l01, l23);
+                    const int trow = wt * 32 + lrow;
+                    const int off = (trow >> 3) * kSBO + (qd >> 1) * kLBO_A1 + (trow & 7) * 16 + (qd & 1) * 8;
+                    *reinterpret_cast<uint2*>(a1h + off) = make_uint2(h[0], h[1]);
+                    *reinterpret_cast<uint2*>(a1l + off) = make_uint2(l[0], l[1]);
                 }
-                __syncwarp();                                               // taps buffer is reused by the next half
+            } else {
+            const char* vq = reinterpret_cast<const char*>(a.planes) + ((long long)view * g.stride_view + 8 * q8) * kEsz;
+            // ---- gather: 4 rounds of 8 rows; lane (q8, rr) loads channels [8 q8, 8 q8 + 8) of the 12 taps of row 8 round + rr in
+            //      two halves of six 256-bit loads (plane 0 + the upper texel row of plane 1 | the lower row of plane 1 + plane 2)
+#pragma unroll 1
+            for (int round = 0; round < 4; ++round) {
+                const int lrow = round * 8 + rr;
+                const uint4 c0 = *reinterpret_cast<const uint4*>(tab + tab_off(lrow, 0));
+                const bool p0 = c0.w & 1u, p1 = c0.w & 2u, p2 = c0.w & 4u;
+                const char* b0 = vq + (unsigned long long)c0.x * kEsz;
+                const char* b1 = vq + (unsigned long long)c0.y * kEsz;
+                const char* b2 = vq + (unsigned long long)c0.z * kEsz;
+                // half 1
+                load_oct<BF16, 0>(v[0], b0, p0);
+                if (SCOL) load_oct<BF16, kImmX>(v[1], b0, p0); else load_oct<BF16, 0>(v[1], b0 + scolB, p0);
+                load_oct<BF16, 0>(v[2], b0 + srowB, p0);
+                if (SCOL) load_oct<BF16, kImmX>(v[3], b0 + srowB, p0); else load_oct<BF16, 0>(v[3], b0 + srowB + scolB, p0);
+                load_oct<BF16, 0>(v[4], b1, p1);
+                if (SCOL) load_oct<BF16, kImmX>(v[5], b1, p1); else load_oct<BF16, 0>(v[5], b1 + scolB, p1);
+                unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+                const float4 w0 = *reinterpret_cast<const float4*>(tab + tab_off(lrow, 1));
+                const float4 w1 = *reinterpret_cast<const float4*>(tab + tab_off(lrow, 2));
+                fma8(acc, v[0], w0.x); fma8(acc, v[1], w0.y); fma8(acc, v[2], w0.z); fma8(acc, v[3], w0.w);
+                fma8(acc, v[4], w1.x); fma8(acc, v[5], w1.y);
+                // half 2
+                load_oct<BF16, 0>(v[0], b1 + srowB, p1);
+                if (SCOL) load_oct<BF16, kImmX>(v[1], b1 + srowB, p1); else load_oct<BF16, 0>(v[1], b1 + srowB + scolB, p1);
+                load_oct<BF16, 0>(v[2], b2, p2);
+                if (SCOL) load_oct<BF16, kImmX>(v[3], b2, p2); else load_oct<BF16, 0>(v[3], b2 + scolB, p2);
+                load_oct<BF16, 0>(v[4], b2 + srowB, p2);
+                if (SCOL) load_oct<BF16, kImmX>(v[5], b2 + srowB, p2); else load_oct<BF16, 0>(v[5], b2 + srowB + scolB, p2);
+                const float4 w2 = *reinterpret_cast<const float4*>(tab + tab_off(lrow, 3));
+                fma8(acc, v[0], w1.z); fma8(acc, v[1], w1.w);
+                fma8(acc, v[2], w2.x); fma8(acc, v[3], w2.y); fma8(acc, v[4], w2.z); fma8(acc, v[5], w2.w);
+                // mean over the planes (the 1/3 is folded into W1), bf16 hi/lo split, one 16 B K-chunk each
+                uint32_t h[4], l[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float e0, e1;
+                    asm("mov.b64 {%0, %1}, %2;" : "=f"(e0), "=f"(e1) : "l"(acc[j]));
+                    split2(e0, e1, h[j], l[j]);
+                }
+                const int trow = wt * 32 + lrow;
+                const int off = (trow >> 3) * kSBO + q8 * kLBO_A1 + (trow & 7) * 16;
+                *reinterpret_cast<uint4*>(a1h + off) = make_uint4(h[0], h[1], h[2], h[3]);
+                *reinterpret_cast<uint4*>(a1l + off) = make_uint4(l[0], l[1], l[2], l[3]);
+            }
             }
             fence_proxy_async();
-            __syncwarp();
+            __syncwarp();                                                   // also: the tap table is rewritten by the next tile
             if (lane == 0) mbar_arrive(&sm.a1_full[stage]);
-            tk_.lap(3);                                                   // [3] taps + gather of one tile (32 rows)
+            tk_.lap(3);                                                   // [3] gather of one tile (32 rows)
         }
     } else if (warp < kGW + kEW) {
         // =========================================================================== EPILOGUE
@@ -701,7 +803,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
                 const int pos = i + lo;
                 m_t[pos] = tv;
                 m_sg[pos] = is_f ? st.sg_f[rl * Sf + i] : st.sg_c[rl * S + ci];
-                sl.pos[is_f ? kRowsG + rl * Sf + i : rl * S + ci] = pos;
+                sl.pos[is_f ? kRowsG + rl * Sf + i : rl * S + ci] = (unsigned short)pos;
             }
             __syncwarp();
             float al[L / 32], inc[L / 32], tm[L / 32];
@@ -813,11 +915,11 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
                 const uint32_t a1h = smem_u32(sm.a1[stage][0]), a1l = smem_u32(sm.a1[stage][1]);
 #pragma unroll
                 for (int ks = 0; ks < kC / 16; ++ks) {
-                    const uint32_t ao = ks * 2 * kLBO_A, bo = ks * 2 * kLBO_W1;
-                    umma_bf16(tmem + kColD1, umma_desc(a1h + ao, kLBO_A, kSBO), umma_desc(w1h + bo, kLBO_W1, kSBO), idesc1, ks > 0);
+                    const uint32_t ao = ks * 2 * kLBO_A1, bo = ks * 2 * kLBO_W1;
+                    umma_bf16(tmem + kColD1, umma_desc(a1h + ao, kLBO_A1, kSBO), umma_desc(w1h + bo, kLBO_W1, kSBO), idesc1, ks > 0);
                     if (!a.single_pass) {
-                        umma_bf16(tmem + kColD1, umma_desc(a1h + ao, kLBO_A, kSBO), umma_desc(w1l + bo, kLBO_W1, kSBO), idesc1, 1);
-                        umma_bf16(tmem + kColD1, umma_desc(a1l + ao, kLBO_A, kSBO), umma_desc(w1h + bo, kLBO_W1, kSBO), idesc1, 1);
+                        umma_bf16(tmem + kColD1, umma_desc(a1h + ao, kLBO_A1, kSBO), umma_desc(w1l + bo, kLBO_W1, kSBO), idesc1, 1);
+                        umma_bf16(tmem + kColD1, umma_desc(a1l + ao, kLBO_A1, kSBO), umma_desc(w1h + bo, kLBO_W1, kSBO), idesc1, 1);
                     }
                 }
                 umma_commit(&sm.d1_full);
@@ -847,6 +949,8 @@ int launch_depth_finalize(float* depth, long long R, const unsigned int* bounds,
 bool fused_ws3_supported(const Geom& g) {
     if (!((g.S == 96 || g.S == 48) && (g.Sf == g.S) && ((long long)g.M % (384 / g.S) == 0))) return false;
     const long long span = 2 * g.stride_plane + (long long)(g.H - 1) * g.stride_row + (long long)(g.W - 1) * g.stride_col + kC;
+    if (g.H < 2 || g.W < 2) return false;
+    if ((g.stride_view | g.stride_plane | g.stride_row | g.stride_col) & 7) return false;
     return g.stride_plane >= 0 && g.stride_row >= 0 && g.stride_col >= 0 && span < (1ll << 31);
 }
 
@@ -890,8 +994,9 @@ int render_forward_fused_ws3(const Geom& g, const p3d_render_params* p, const vo
     }
     const size_t smem = sizeof(WsSmem) + 1024;
     void (*kern)(WsArgs) = nullptr;
-    if (g.S == 96) kern = p->planes_bf16 ? k_render_ws3<true, 96> : k_render_ws3<false, 96>;
-    else kern = p->planes_bf16 ? k_render_ws3<true, 48> : k_render_ws3<false, 48>;
+    const bool sc32 = g.stride_col == kC;
+    if (g.S == 96) kern = p->planes_bf16 ? (sc32 ? k_render_ws3<true, 96, kC> : k_render_ws3<true, 96, 0>) : (sc32 ? k_render_ws3<false, 96, kC> : k_render_ws3<false, 96, 0>);
+    else kern = p->planes_bf16 ? (sc32 ? k_render_ws3<true, 48, kC> : k_render_ws3<true, 48, 0>) : (sc32 ? k_render_ws3<false, 48, kC> : k_render_ws3<false, 48, 0>);
     P3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = a.n_groups < n_sm ? a.n_groups : n_sm;
     {

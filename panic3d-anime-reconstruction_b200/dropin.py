@@ -155,7 +155,18 @@ def enable_plane_reuse(G, default_noise_mode='const'):
     ``default_noise_mode``: the noise mode given to backbone calls that do not name one ('const': deterministic sweep,
     cacheable - differs from the reference, which redraws the layer noise for every view; None: keep the reference's
     per-call random noise, in which case only calls that explicitly ask for 'const' / 'none' are cached)."""
+    import torch
     syn = G.backbone.synthesis
+    if isinstance(syn, torch.nn.Module):
+        # the real backbone: `synthesis` is a registered sub-module (networks_stylegan2.SynthesisNetwork), so it cannot be
+        # replaced by a plain callable - the memo goes in front of its forward instead (instance attribute; Module.__call__
+        # and hooks keep working, state_dict is untouched)
+        memo = getattr(syn, '_p3d_plane_memo', None)
+        if memo is None:
+            memo = _PlaneMemo(syn.forward, default_noise_mode)
+            syn.forward = memo
+            syn._p3d_plane_memo = memo
+        return memo
     if isinstance(syn, _PlaneMemo):
         return syn
     memo = _PlaneMemo(syn, default_noise_mode)
