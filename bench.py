@@ -31,6 +31,9 @@ UNIT = 'views/s'
 R, S, SF, P, C, VIEWS = 128, 96, 96, 512, 32, 8
 FLOP_PER_SAMPLE = 2 * 32 * 64 + 2 * 64 * 33            # 8,320 tensor-eligible FLOP
 BYTES_PER_VIEW = 3 * C * P * P * 4 + R * R * 37 * 4    # tri-plane read once + 37 floats/ray out
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the default fused kernel on this workload, from the committed
+# `ncu --set full` capture (profiles/r2_ws3_raw.csv)
+FUSED_TRAFFIC = 652.7e6
 
 
 # rendering_options of BASELINE configs[1] (train_eclustrousC.py:409-440 + eg3dc_v0.py:30-31,55-56)
@@ -253,15 +256,24 @@ def run_ours(args):
     renderer, sampler = ImportanceRenderer(use_triplane=True), RaySampler()
     renderer.mlp_mode = mlp_mode
     renderer.planes_bf16 = args.planes == 'bf16'
-    gather_buf = torch.empty((world * VIEWS, R * R, 32), device=dev) if world > 1 else None
+    # rendered images -> rank 0 (BASELINE configs[3]): peer-to-peer DMA into rank 0's buffer on a side stream (views.PeerGather),
+    # overlapped with the next step's render; P3D_BENCH_GATHER=nccl selects the blocking NCCL all-gather of round 1 for A/B
+    from panic3d_b200 import views as pviews
+    gather_mode = os.environ.get('P3D_BENCH_GATHER', 'p2p') if world > 1 else 'none'
+    gather_buf = torch.empty((world * VIEWS, R * R, 32), device=dev) if gather_mode == 'nccl' else None
+    peer = pviews.PeerGather((VIEWS, R * R, 32), torch.float32, dev, dst=0) if gather_mode == 'p2p' else None
+    step_no = [0]
 
     def step():
         c2w, K = labels_dev[:, :16].view(-1, 4, 4), labels_dev[:, 16:25].view(-1, 3, 3)
         ro, rd = sampler(c2w, K, R)
         renderer._planes.key = None                                           # distinct tri-planes every step: redo the layout pass
         rgb, depth, wsum, xyz = renderer(planes, decoder, ro, rd, opts)
-        if world > 1:                                                            # rendered images -> every rank (rank 0 consumes them)
+        if gather_mode == 'nccl':
             dist.all_gather_into_tensor(gather_buf, rgb)
+        elif gather_mode == 'p2p':
+            peer.push(rgb, step_no[0])
+            step_no[0] += 1
         return rgb
 
     def barrier():
@@ -281,6 +293,8 @@ def run_ours(args):
         e0.record()
         for _ in range(args.steps):
             step()
+        if peer is not None:
+            peer.join_current_stream()                                          # the last image copies are inside the bracket
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -325,6 +339,28 @@ def run_ours(args):
                 variants[name] = {'value': round(VIEWS * 10 / (v0.elapsed_time(v1) * 1e-3), 1), 'unit': UNIT, 'steps': 10}
                 del rv
         if variants is not None:
+            # the tri-planes arrive as a (N,96,H,W) torch.channels_last tensor (what a channels-last backbone emits): the renderer
+            # reads them in place - no layout pre-pass, the step moves only the algorithmic bytes
+            pl_cl = planes.reshape(VIEWS, 3 * C, P, P).contiguous(memory_format=torch.channels_last).view(VIEWS, 3, C, P, P)
+            rv = ImportanceRenderer(use_triplane=True)
+            rv.mlp_mode = mlp_mode
+
+            def zstep():
+                c2w, K = labels_dev[:, :16].view(-1, 4, 4), labels_dev[:, 16:25].view(-1, 3, 3)
+                ro, rd = sampler(c2w, K, R)
+                return rv(pl_cl, decoder, ro, rd, opts)
+            for _ in range(3):
+                zstep()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            v0.record()
+            for _ in range(10):
+                zstep()
+            v1.record()
+            torch.cuda.synchronize()
+            variants['channels_last tri-planes consumed zero-copy (no layout pre-pass)'] = {'value': round(VIEWS * 10 / (v0.elapsed_time(v1) * 1e-3), 1), 'unit': UNIT, 'steps': 10}
+            del rv, pl_cl
+            torch.cuda.empty_cache()
             # the 256^3 sigma/rgb grid of get_eg3d_volume for one subject, one launch (reference: 168 chunks)
             from panic3d_b200 import volume as pvol
             for _ in range(2):
@@ -396,6 +432,25 @@ def run_ours(args):
         if not args.no_e2e:
             e2e = run_e2e(L, _lib, planes, decoder, labels, opts, mlp_mode, args, barrier)
 
+    comm_ms = None
+    if world > 1:                                                    # the exchange alone (device time, max over ranks), for the `comm` field
+        with torch.no_grad():
+            rgb_probe = step()
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for i in range(5):
+                if gather_mode == 'nccl':
+                    dist.all_gather_into_tensor(gather_buf, rgb_probe)
+                else:
+                    peer.push(rgb_probe, i)
+            if peer is not None:
+                peer.join_current_stream()
+            c1.record()
+            barrier()
+            tc = torch.tensor([c0.elapsed_time(c1) / 5], device=dev, dtype=torch.float64)
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+            comm_ms = float(tc.item())
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -423,9 +478,9 @@ def run_ours(args):
             roof = {'bound': 'hbm', 'achieved': byts / (kern_ms * 1e-3) / 1e9, 'peak': hbm_gbs, 'unit': 'GB/s'}
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
         # command (profiles/r1_final_ws_raw.csv: 630.5 MB + 22.3 MB); only valid for the default kernel / workload
-        traffic = 652.7e6 if (fused and args.planes == 'fp32' and os.environ.get('P3D_FUSED_IMPL', '') != 'v2') else None
+        traffic = FUSED_TRAFFIC if (fused and args.planes == 'fp32' and os.environ.get('P3D_FUSED_IMPL', 'v5') == 'v5') else None
         roof.update({'frac': roof['achieved'] / roof['peak'], 'traffic': traffic,
-                     'kernel': ('k_render_ws' if os.environ.get('P3D_FUSED_IMPL', '') != 'v2' else 'k_render_fused') if fused else 'k_sample_decode',
+                     'kernel': ('k_render_ws3' if os.environ.get('P3D_FUSED_IMPL', 'v5') == 'v5' else 'k_render_ws') if fused else 'k_sample_decode',
                      'kernel_ms_per_launch': kern_ms,
                      'launches_timed': int(slot_n[slot]), 'peak_source': peak_src,
                      'step_breakdown_ms': {'sample_decode': slot_ms[0] / 3, 'importance': slot_ms[1] / 3, 'composite': slot_ms[2] / 3,
@@ -434,6 +489,9 @@ def run_ours(args):
                'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world, args.mlp, args.planes), 'clocks': clocks,
                'gpu_launches': int(launches), 'roofline': roof}
+        if world > 1:
+            out['comm'] = {'mode': gather_mode, 'bytes_per_rank_per_step': VIEWS * R * R * 32 * 4, 'ms_per_step': comm_ms,
+                           'note': 'rendered feature images -> rank 0; p2p = NVLink DMA on a side stream under the next render'}
         if e2e is not None:
             out['e2e'] = {'value': world * VIEWS * e2e['steps'] / (e2e['ms'] * 1e-3), 'unit': UNIT,
                           'h2d_bytes_per_step': e2e['h2d'], 'd2h_bytes_per_step': e2e['d2h'], 'steps': e2e['steps'],

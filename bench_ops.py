@@ -52,9 +52,19 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--only', default='', help='substring filter on "op case"')
     ap.add_argument('--dtypes', default='float16,float32')
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'],
+                    help="reference: the UNMODIFIED ops of baseline/_ref with their own JIT CUDA plugins (prebuilt by baseline/install_ref.sh), "
+                         "timed on the same GPU for the per-op comparison")
     args = ap.parse_args()
-    import panic3d_b200  # noqa: F401
-    from panic3d_b200.torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu
+    if args.impl == 'reference':
+        ref = os.path.join(ROOT, 'baseline', '_ref')
+        os.environ.setdefault('TORCH_EXTENSIONS_DIR', os.path.join(ref, '_torch_ext'))
+        sys.path.insert(0, os.path.join(ref, '_train', 'eg3dc', 'src'))
+        from torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu
+        assert 'baseline/_ref' in bias_act.__file__.replace(os.sep, '/')
+    else:
+        import panic3d_b200  # noqa: F401
+        from panic3d_b200.torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu
     dev = torch.device('cuda:0')
     peak, src = hbm_peak()
     flush = torch.zeros(192 * 1024 * 1024 // 4, device=dev)          # 192 MB > 126 MB L2
@@ -68,7 +78,7 @@ def main():
         esz = torch.finfo(dtype).bits // 8
         ms = timeit(fn, flush)
         byts = (x_elems + y_elems) * esz
-        r = {'op': op, 'case': case, 'dtype': str(dtype).split('.')[-1], 'ms': round(ms, 4), 'algorithmic_bytes': byts,
+        r = {'impl': args.impl, 'op': op, 'case': case, 'dtype': str(dtype).split('.')[-1], 'ms': round(ms, 4), 'algorithmic_bytes': byts,
              'gbs': round(byts / ms / 1e6, 1), 'frac_of_hbm_peak': round(byts / ms / 1e6 / peak, 3), 'peak': f'{peak} GB/s ({src})'}
         out.append(r)
         print(json.dumps(r), flush=True)
@@ -109,7 +119,7 @@ def main():
                 lambda: filtered_lrelu.filtered_lrelu(x, f12, f12, b, up=2, down=2, padding=[9, 10, 9, 10], clamp=256))
             del x, y
     os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
-    json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'bench_ops.json'), 'w'), indent=1)
+    json.dump(out, open(os.path.join(ROOT, 'gpurun_out', 'bench_ops.json' if args.impl == 'ours' else 'bench_ops_ref.json'), 'w'), indent=1)
 
 
 if __name__ == '__main__':

@@ -372,7 +372,7 @@ size_t p3d_render_workspace_bytes(const p3d_render_params* p) {
 int p3d_render_fused_supported(const p3d_render_params* p) {
     Geom g;
     if (!p || make_geom(p, &g)) return 0;
-    return fused_ws_supported(g) ? 1 : 0;
+    return (fused_ws3_supported(g) || fused_ws_supported(g)) ? 1 : 0;
 }
 
 int p3d_render_forward(const p3d_render_params* p, const void* planes, const float* w1, const float* b1, const float* w2,
@@ -397,17 +397,17 @@ int p3d_render_forward(const p3d_render_params* p, const void* planes, const flo
         return render_forward_v1(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
                                  out_depth, out_wsum, out_xyz, (cudaStream_t)stream);
     if (p->mlp_mode == P3D_MLP_TC_3XBF16 || p->mlp_mode == P3D_MLP_TC_BF16) {
-        static const char* impl = getenv("P3D_FUSED_IMPL");       // "v2": 2-CTA/SM bulk-synchronous kernel; default: warp-specialised
-        if (impl && impl[0] == 'v' && impl[1] == '5' && fused_ws3_supported(g))                 // experimental, opt-in only
+        // P3D_FUSED_IMPL selects among the fused kernels for A/B runs (read once per process):
+        //   (default) "v5"  render_fused_ws3.cu  warp-specialised, pipeline depth 3, dedicated ray warps
+        //             "v3"  render_fused_ws.cu   warp-specialised, two ray groups in flight (round-1 design + the round-2 gather)
+        static const char* impl = getenv("P3D_FUSED_IMPL");
+        const char which = (impl && impl[0] == 'v') ? impl[1] : '5';
+        if (which == '5' && fused_ws3_supported(g))
             return render_forward_fused_ws3(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
                                             out_depth, out_wsum, out_xyz, (cudaStream_t)stream);
-        if (!(impl && impl[0] == 'v' && impl[1] == '2') && fused_ws_supported(g))
-            return render_forward_fused_ws(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
-                                           out_depth, out_wsum, out_xyz, (cudaStream_t)stream);
+        return render_forward_fused_ws(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
+                                       out_depth, out_wsum, out_xyz, (cudaStream_t)stream);     // P3D_EUNSUPPORTED when it has no kernel either
     }
-    if (p->mlp_mode == P3D_MLP_TC_3XBF16 || p->mlp_mode == P3D_MLP_TC_BF16)
-        return render_forward_fused(g, p, planes, w1, b1, w2, b2, ray_origins, ray_dirs, u_coarse, u_fine, ws, out_rgb,
-                                    out_depth, out_wsum, out_xyz, (cudaStream_t)stream);
     set_error("mlp_mode %d has no kernel in this build", p->mlp_mode);
     return P3D_EUNSUPPORTED;
 }
@@ -496,11 +496,19 @@ int p3d_render_forward_host(const p3d_render_params* p_in, const float* planes_n
     // fp32 against ~1 ms of rendering), so views are pipelined over three streams: H2D of view v+1 overlaps layout +
     // rendering of view v, whose rgb / weights / xyz start their D2H while view v+1 renders.  Each view is one
     // p3d_render_forward call with defer_depth_clamp; the batch-wide depth clamp (ray_marcher.py:50) is applied once
-    // at the end from the merged per-view bounds, so results equal the one-shot call on the whole batch.
+    // at the end from the merged per-view bounds, so results equal the one-shot call on the whole batch.  That holds for
+    // numeric ray limits only: with 'auto' limits the reference fills the rays that miss the box with the min / max start
+    // of the WHOLE batch (renderer.py:167-170), a second batch-wide reduction this per-view pipeline does not carry -
+    // P3D_RAYS_AUTOBOX is rejected here (use p3d_render_forward on device buffers for it).
     P3D_REQUIRE(p_in && planes_nchw && w1 && b1 && w2 && b2 && cam2world && intrinsics, "null input pointer");
     P3D_REQUIRE(out_rgb && out_depth && out_wsum && out_xyz, "null output pointer");
     p3d_render_params p = *p_in;
     P3D_REQUIRE(p.n_rays == resolution * resolution, "n_rays must equal resolution^2");
+    if (p.ray_mode == P3D_RAYS_AUTOBOX) {
+        set_error("p3d_render_forward_host renders view by view and cannot reproduce the batch-wide fill of 'auto' ray limits "
+                  "(renderer.py:167-170); pass numeric ray_start / ray_end or call p3d_render_forward on the whole batch");
+        return P3D_EUNSUPPORTED;
+    }
     P3D_REQUIRE(p.n_views >= 0, "bad sizes");
     if ((long long)p.n_views * p.n_rays == 0) return P3D_OK;
     std::lock_guard<std::mutex> lock(g_arena.mu);

@@ -1,8 +1,5 @@
-// EXPERIMENTAL - NOT VALIDATED ON HARDWARE YET (written after the round's GPU budget was spent; opt-in only through
-// P3D_FUSED_IMPL=v5, never selected by default, no parity claim until tests/test_render_gpu.py has run against it).
-//
-// Warp-specialised fused renderer, pipeline depth 3 ("v5").  Same roles and arithmetic as render_fused_ws.cu plus the
-// dedicated RAY warps of the round-1 experiment (profiles/experiments/render_fused_ws_rayroles_v4.cu.txt), but the
+// The default fused renderer (round 2): warp-specialised, pipeline depth 3 ("v5").  Same roles and arithmetic as
+// render_fused_ws.cu plus dedicated RAY warps, but the
 // colour logits are parked differently so that THREE ray groups are in flight instead of two:
 //
 //   TMEM   D1 [0,64) | sigma [64,80) | coarse areas CA[a] = [96 + 96a, +96), a = n % 3 | fine area FA = [384, 480)
@@ -45,6 +42,17 @@ __device__ __forceinline__ uint32_t d2_col(int n, int pass, int k) { return (uin
 
 constexpr int kSBO = 128, kLBO_A = 2048, kLBO_A1 = 2080, kLBO_W1 = 1024, kLBO_W2C = 512, kLBO_W2S = 256;
 constexpr bool kG256 = false;
+// build-time A/B switches (profiles/r2_kernel_log.md); the defaults are what ships
+#ifndef P3D_W3_WAIT
+#define P3D_W3_WAIT 0          // 0: try_wait with a suspend-time hint, bounded (traps on a protocol bug); 2: plain try_wait, bounded (measured slower)
+#endif
+#ifndef P3D_W3_LG2POLY
+#define P3D_W3_LG2POLY 0       // 1: the lg2(1 + t) half of the tile epilogue's softplus as a packed polynomial on the FMA pipe (needs P3D_W3_SOFTPLUS)
+#endif
+#ifndef P3D_W3_SOFTPLUS
+#define P3D_W3_SOFTPLUS 1      // 1: guard-free softplus max(x,0) + lg2(1 + 2^-|x|) with packed f32x2 adds and a packed hi/lo split
+#endif
+
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
 struct GroupState {                               // written by G (t_c, crop), E (sg_*), R (t_f)
@@ -54,6 +62,8 @@ struct GroupState {                               // written by G (t_c, crop), E
 struct SlotState {                                // written by R (composite), read by E (colours)
     float om[2 * kRowsG];                         // omega per merged position, [ray][2S]
     unsigned short pos[2 * kRowsG];                          // merged position of coarse rows [0,384) and fine rows [384,768)
+    float acc[8][kRgb];
+    float back[8];
 };
 
 struct __align__(1024) WsSmem {
@@ -68,8 +78,7 @@ struct __align__(1024) WsSmem {
     unsigned long long a1_full[kNA], a1_empty[kNA], a2_full[2], a2_empty[2];
     unsigned long long d1_full, d1_empty, d2_full, dsig_empty;
     unsigned long long fine_ready[kStates], state_free[kStates];
-    unsigned long long sigc_ready[kStates], sigf_ready[kStates];   // E -> R (sigma of a pass is in shared memory)
-    unsigned long long fa_free;                                    // R -> MMA: the colours of the last fine pass have left TMEM
+    unsigned long long sigc_ready[kStates], sigf_ready[kStates], omega_ready[2];   // E -> R (sigma in smem), R -> E (omega)
     unsigned int tmem_base, pad1;
 };
 
@@ -105,6 +114,18 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+#if P3D_W3_WAIT == 2
+#pragma unroll 1
+    for (int it = 0; it < (1 << 24); ++it) {             // plain try_wait: the hardware's own suspend window per try; still bounded
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    asm volatile("trap;");
+#endif
+    // (not unrolled: ptxas otherwise replicates the body 16x at each of the ~50 call sites - half of the kernel's code size)
+#pragma unroll 1
     for (int it = 0; it < (1 << 17); ++it) {             // ~20 us per try: the cap turns a protocol bug into a trap after ~2 s
         uint32_t ok;
         // the suspend-time hint lets a waiting warp sleep in hardware instead of polling: roles that run ahead of the
@@ -148,17 +169,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
         : "r"(taddr) : "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
     uint32_t r;
@@ -226,6 +236,35 @@ __device__ __forceinline__ void load_oct(float (&v)[8], const char* addr, bool p
                      : "l"(addr), "r"((int)pred), "n"(IMM));
     }
 }
+// packed f32x2 arithmetic (one instruction for two lanes of data)
+__device__ __forceinline__ unsigned long long pk2(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// lg2(1 + t) for t in [0, 1] on the FMA pipe, two values per instruction: t * q(t), q = degree-6 near-minimax fit of
+// lg2(1 + t) / t (max abs error 1.4e-6 in fp32 Horner form, exact 0 at t = 0).  Takes the second MUFU of every softplus off the
+// MUFU / MIO queue, which is what throttles the tile epilogue (ncu: mio_throttle on the softplus lines).
+__device__ __forceinline__ unsigned long long lg2_1p_poly2(unsigned long long t) {
+    unsigned long long q = fma2(t, pk2(0.020490340888500214f, 0.020490340888500214f), pk2(-0.09606623649597168f, -0.09606623649597168f));
+    q = fma2(t, q, pk2(0.2155885100364685f, 0.2155885100364685f));
+    q = fma2(t, q, pk2(-0.33924776315689087f, -0.33924776315689087f));
+    q = fma2(t, q, pk2(0.4777059257030487f, 0.4777059257030487f));
+    q = fma2(t, q, pk2(-0.721162736415863f, -0.721162736415863f));
+    q = fma2(t, q, pk2(1.4426932334899902f, 1.4426932334899902f));
+    return mul2(t, q);
+}
+// (h0, h1) -> bf16x2 hi word and bf16x2 lo word of the residuals, 4 instructions + the pack
+__device__ __forceinline__ void split2p(unsigned long long h2, uint32_t& hi, uint32_t& lo) {
+    float h0, h1;
+    upk2(h2, h0, h1);
+    hi = pack_bf16x2(h0, h1);
+    const unsigned long long r2 = sub2(h2, pk2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)));
+    float r0, r1;
+    upk2(r2, r0, r1);
+    lo = pack_bf16x2(r0, r1);
+}
 // four consecutive channels of one texel (16 B fp32 / 8 B bf16) at addr + IMM bytes, predicated; v keeps its old value when !pred
 template <bool BF16, int IMM>
 __device__ __forceinline__ void load_quad_p(float (&v)[4], const char* addr, bool pred) {
@@ -233,7 +272,7 @@ __device__ __forceinline__ void load_quad_p(float (&v)[4], const char* addr, boo
         uint32_t r0 = 0, r1 = 0;
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p ld.global.nc.v2.u32 {%0,%1}, [%2+%4];\n\t}"
                      : "+r"(r0), "+r"(r1) : "l"(addr), "r"((int)pred), "n"(IMM));
-        if (pred) { v[0] = __uint_as_float(r0 << 16); v[1] = __uint_as_float(r0 & 0xffff0000u); v[2] = __uint_as_float(r1 << 16); v[3] = __uint_as_float(r1 & 0xffff0000u); }
+        v[0] = __uint_as_float(r0 << 16); v[1] = __uint_as_float(r0 & 0xffff0000u); v[2] = __uint_as_float(r1 << 16); v[3] = __uint_as_float(r1 & 0xffff0000u);   // zeros when !pred
     } else {
         asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4+%6];\n\t}"
                      : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) : "l"(addr), "r"((int)pred), "n"(IMM));
@@ -302,10 +341,10 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
         for (int i = 0; i < 2; ++i) { mbar_init(&sm.a2_full[i], kEW); mbar_init(&sm.a2_empty[i], 1); }
         mbar_init(&sm.d1_full, 1); mbar_init(&sm.d1_empty, kEW); mbar_init(&sm.d2_full, 1); mbar_init(&sm.dsig_empty, 4);
         for (int i = 0; i < kStates; ++i) {
-            mbar_init(&sm.fine_ready[i], kRW); mbar_init(&sm.state_free[i], kRW);
+            mbar_init(&sm.fine_ready[i], kRW); mbar_init(&sm.state_free[i], 1);
             mbar_init(&sm.sigc_ready[i], 4); mbar_init(&sm.sigf_ready[i], 4);      // the four chunk-0 epilogue warps
         }
-        mbar_init(&sm.fa_free, kRW);
+        mbar_init(&sm.omega_ready[0], kRW); mbar_init(&sm.omega_ready[1], kRW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < kHidden * kC; i += kThreadsWS) {            // W1' = W1 * gain * log2(e)   (64 x 32)
@@ -434,15 +473,17 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
                     const char* b0 = vq4 + (unsigned long long)c0.x * kEsz;
                     const char* b1 = vq4 + (unsigned long long)c0.y * kEsz;
                     const char* b2 = vq4 + (unsigned long long)c0.z * kEsz;
-#define P3D_LD4(k, base, pr)                                                                                         \
+#define P3D_ROW1(base, rbase) (base + srowB)
+#define P3D_LD4(k, base, rbase, pr)                                                                                  \
                     load_quad_p<BF16, 0>(v4[k], base, pr);                                                            \
                     if (SCOL) load_quad_p<BF16, kImmX4>(v4[k + 1], base, pr); else load_quad_p<BF16, 0>(v4[k + 1], base + scolB, pr); \
-                    load_quad_p<BF16, 0>(v4[k + 2], base + srowB, pr);                                                \
-                    if (SCOL) load_quad_p<BF16, kImmX4>(v4[k + 3], base + srowB, pr); else load_quad_p<BF16, 0>(v4[k + 3], base + srowB + scolB, pr);
-                    P3D_LD4(0, b0, p0)
-                    P3D_LD4(4, b1, p1)
-                    P3D_LD4(8, b2, p2)
+                    load_quad_p<BF16, 0>(v4[k + 2], P3D_ROW1(base, rbase), pr);                                       \
+                    if (SCOL) load_quad_p<BF16, kImmX4>(v4[k + 3], P3D_ROW1(base, rbase), pr); else load_quad_p<BF16, 0>(v4[k + 3], P3D_ROW1(base, rbase) + scolB, pr);
+                    P3D_LD4(0, b0, r0, p0)
+                    P3D_LD4(4, b1, r1, p1)
+                    P3D_LD4(8, b2, r2, p2)
 #undef P3D_LD4
+#undef P3D_ROW1
                     const float4 w0 = *reinterpret_cast<const float4*>(tab + tab_off(lrow, 1));
                     const float4 w1 = *reinterpret_cast<const float4*>(tab + tab_off(lrow, 2));
                     const float4 w2 = *reinterpret_cast<const float4*>(tab + tab_off(lrow, 3));
@@ -543,8 +584,65 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             }
         };
         auto ebar = [] { asm volatile("bar.sync 1, 256;" ::: "memory"); };   // the eight epilogue warps
-        // the epilogue warps only convert tiles (D1 -> A2) and read sigma back; everything per ray - importance sampling,
-        // merge / transmittance and the colour reduction out of TMEM - belongs to the ray warps
+        auto colours = [&](int n) {                                        // sum_j omega_j * rgb_j for group n, from TMEM
+            const int slot_i = n & 1;
+            SlotState& sl = sm.slot[slot_i];
+            mbar_wait(&sm.omega_ready[slot_i], (n >> 1) & 1);              // omega / pos / back of group n (ray warps)
+            tc_fence_after();
+            const int grp = (int)blockIdx.x + n * (int)gridDim.x;
+            const long long ray0 = (long long)grp * GR;
+            // A warp's 32 TMEM rows are the same ray(s) in each of its three tiles, so the per-tile column sums are
+            // first added up in a register and published once: every (ray, channel) cell of sl.acc then receives
+            // exactly two shared-memory adds (one per chunk), whose order cannot change the rounded sum - the kernel
+            // is bit-reproducible run to run and independent of how the rays are batched.
+            float part[2] = {0.f, 0.f};
+            const int rl_first = (quarter * 32) / RPT;
+            for (int i = 0; i < 3; ++i) {
+                const int tile6 = chunk + 2 * i;                           // this warp's tiles: {0,2,4} or {1,3,5}
+                const int pass = tile6 / 3, k = tile6 - pass * 3;
+                const int trow = quarter * 32 + lane;
+                const int rl = trow / RPT, s = k * RPT + (trow - rl * RPT);
+                const bool live = ray0 + rl < a.R;
+                const float om = live ? sl.om[rl * L + sl.pos[pass * kRowsG + rl * S + s]] : 0.f;
+                const float ca = g.force_sigmoid ? om : 1.002f * om, cb = g.force_sigmoid ? 0.f : -0.001f * om;
+                float v[32];
+                tmem_ld32(tmem + d2_col(n, pass, k) + lane_base, v);
+#pragma unroll
+                for (int c = 0; c < kRgb; ++c) v[c] = fmaf(rcp_approx(1.f + ex2_approx(v[c] + sm.b2c[c])), ca, cb);
+#pragma unroll
+                for (int t2 = 0; t2 < 32 / RPT; ++t2) {
+                    const int target = rl_first + t2;
+                    float r[32];
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) r[c] = (RPT == 32 || rl == target) ? v[c] : 0.f;
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int j = 0; j < off; ++j) {
+                            const float send = up ? r[j] : r[j + off];
+                            const float keep = up ? r[j + off] : r[j];
+                            r[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    part[t2] += r[0];
+                }
+            }
+#pragma unroll
+            for (int t2 = 0; t2 < 32 / RPT; ++t2) atomicAdd(&sl.acc[rl_first + t2][lane], part[t2]);
+            tc_fence_before();
+            asm volatile("bar.sync 1, 256;" ::: "memory");                 // all eight epilogue warps
+            if (etid < GR * kRgb) {
+                const int rl = etid >> 5, c = etid & 31;
+                const long long ray = ray0 + rl;
+                if (ray < a.R) a.out_rgb[ray * kRgb + c] = __fsub_rn(__fmul_rn(__fadd_rn(sl.acc[rl][c], sl.back[rl]), 2.f), 1.f);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (etid == 0) mbar_arrive(&sm.state_free[n & 3]);
+        };
+
+        // colours(n) needs omega from the ray warps; it runs at the top of the first tile of F(n+1) - three tiles (C(n+2))
+        // after the group's last sigma - which is also the last point before layer 2 of F(n+1) overwrites the fine area.
         Tick tk_(a.timing, blockIdx.x == 0 && e == 0 && lane == 0);
         auto after_sigma_t = [&](const TileDesc&) {};
         int it = 0;
@@ -554,6 +652,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             const TileDesc td = tile_at(q, n_my);
             // ---- epilogue 1: D1 -> softplus2 -> A2[buf]
             tk_.lap(4);
+            if (td.pass == 1 && td.k == 0 && td.n >= 1) { colours(td.n - 1); tk_.lap(11); }   // [11] colours (incl. wait for omega)
             mbar_wait(&sm.d1_full, it & 1);
             tk_.lap(5);                                                   // [5] wait d1_full
             tc_fence_after();
@@ -576,7 +675,23 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
 #pragma unroll
                     for (int x = 0; x < 4; ++x) {
                         const int j = c8 * 8 + 2 * x;
+#if P3D_W3_SOFTPLUS
+                        // softplus2(x) = max(x, 0) + lg2(1 + 2^-|x|): no overflow for any x, so no threshold select; the two adds
+                        // of a column pair are packed
+                        const unsigned long long x2 = add2(pk2(v[j], v[j + 1]), *reinterpret_cast<const unsigned long long*>(&sm.b1[32 * chunk + j]));
+                        float x0, x1;
+                        upk2(x2, x0, x1);
+#if P3D_W3_LG2POLY
+                        split2p(add2(pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)), lg2_1p_poly2(pk2(ex2_approx(-fabsf(x0)), ex2_approx(-fabsf(x1))))), ph[x], pl[x]);
+#else
+                        const unsigned long long u2 = add2(pk2(ex2_approx(-fabsf(x0)), ex2_approx(-fabsf(x1))), pk2(1.f, 1.f));
+                        float u0, u1;
+                        upk2(u2, u0, u1);
+                        split2p(add2(pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)), pk2(lg2_approx(u0), lg2_approx(u1))), ph[x], pl[x]);
+#endif
+#else
                         split2(softplus2(v[j] + sm.b1[32 * chunk + j]), softplus2(v[j + 1] + sm.b1[32 * chunk + j + 1]), ph[x], pl[x]);
+#endif
                     }
                     const int off = tile_off(trow, 32 * chunk + 8 * c8, kLBO_A);
                     *reinterpret_cast<uint4*>(a2h + off) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
@@ -591,11 +706,13 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             if (have_prev) { sigma_read(it - 1, prev); tk_.lap(12); after_sigma_t(prev); }   // [12] sigma read-back (incl. wait d2_full)
             prev = td; have_prev = true;
             ++it;
-            // last tile of a pass: its sigma completes the group's hand-off to the ray warps (and, for the odd tail group,
-            // the next tile in the sequence depends on it), so it is not deferred behind the next tile's layer 1
+            // last tile of a pass: its sigma completes the group's hand-off to the ray warps (and, at the tail, the next tile
+            // depends on it), so it is read at once.  (Deferring it behind the next tile's conversion like the other tiles'
+            // was measured: 3.66 ms vs 3.60 ms per launch - the ray warps lose the slack the epilogue gains.)
             if (td.k == 2) { sigma_read(it - 1, prev); tk_.lap(12); after_sigma_t(prev); have_prev = false; }
         }
         if (have_prev) { sigma_read(it - 1, prev); after_sigma_t(prev); }
+        colours(n_my - 1);
     } else if (warp < kGW + kEW + kRW) {
         // =========================================================================== RAY (one warp per ray)
         const int rw = warp - kGW - kEW;
@@ -724,7 +841,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             __syncwarp();
         };
         // ---- merge + transmittance + omega + per-ray outputs of ray rl of group n (renderer.py:289-301, ray_marcher.py:25-57)
-        auto composite_ray = [&](int n, int rl) -> float {
+        auto composite_ray = [&](int n, int rl) {
             GroupState& st = sm.st[n & 3];
             SlotState& sl = sm.slot[n & 1];
             const long long ray = (long long)((int)blockIdx.x + n * (int)gridDim.x) * GR + rl;
@@ -735,6 +852,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             const bool rev = tc[0] > tc[S - 1];
             const float* tca = rev ? tc + (S - 1) : tc;     // ascending view of the coarse depths: tca[m * dir]
             const int dir = rev ? -1 : 1;
+            sl.acc[rl][lane] = 0.f;
 #pragma unroll
             for (int c = 0; c < L / 32; ++c) {    // merge by rank: position = own index + count of the other list before it
                 const int r = c * 32 + lane;
@@ -801,63 +919,8 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
                     atomicMax(&a.bounds[1], float_to_ordered(m_t[L - 1]));
                 }
             }
+            if (lane == 0) sl.back[rl] = back;
             __syncwarp();
-            return back;
-        };
-        // ---- colour reduction of this warp's TMEM lane quarter (= its ray at S = 96, its two rays at S = 48): sum_j omega_j c_j over
-        //      the six parked tiles of group n, straight out of TMEM, 16 columns at a time; the rows are reduced with one
-        //      transposing butterfly per half, so the result is bit-reproducible (fixed order, no atomics)
-        const uint32_t lane_base_r = (uint32_t)(rw * 32) << 16;
-        auto colours_quarter = [&](int n, const float (&back)[32 / RPT]) {
-            SlotState& sl = sm.slot[n & 1];
-            const int grp = (int)blockIdx.x + n * (int)gridDim.x;
-            const long long ray0 = (long long)grp * GR;
-            const int trow = rw * 32 + lane;
-            const int rl = trow / RPT, s_in = trow - rl * RPT;
-            const bool live = ray0 + rl < a.R;
-            float ca[6], cb[6];
-#pragma unroll
-            for (int t6 = 0; t6 < 6; ++t6) {
-                const int pass = t6 / 3, k = t6 - pass * 3;
-                const float om = live ? sl.om[rl * L + sl.pos[pass * kRowsG + rl * S + k * RPT + s_in]] : 0.f;
-                ca[t6] = g.force_sigmoid ? om : 1.002f * om; cb[t6] = g.force_sigmoid ? 0.f : -0.001f * om;
-            }
-            tc_fence_after();
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                float r[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) r[c] = 0.f;
-#pragma unroll
-                for (int t6 = 0; t6 < 6; ++t6) {
-                    float v[16];
-                    tmem_ld16(tmem + d2_col(n, t6 / 3, t6 % 3) + 16 * h + lane_base_r, v);
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) r[c] += fmaf(rcp_approx(1.f + ex2_approx(v[c] + sm.b2c[16 * h + c])), ca[t6], cb[t6]);
-                }
-#pragma unroll
-                for (int st = 0; st < 4; ++st) {
-                    const int off = (RPT == 32 ? 16 : 8) >> st, n2 = 8 >> st;
-                    const bool up = (lane & off) != 0;
-#pragma unroll
-                    for (int j = 0; j < n2; ++j) {
-                        const float send = up ? r[j] : r[j + n2];
-                        const float keep = up ? r[j + n2] : r[j];
-                        r[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                    }
-                }
-                if (RPT == 32) {
-                    r[0] += __shfl_xor_sync(0xffffffffu, r[0], 1);
-                    const long long ray = ray0 + rw;
-                    if ((lane & 1) == 0 && ray < a.R)
-                        a.out_rgb[ray * kRgb + 16 * h + (lane >> 1)] = __fsub_rn(__fmul_rn(__fadd_rn(r[0], back[0]), 2.f), 1.f);
-                } else {
-                    const long long ray = ray0 + rw * 2 + (lane >> 4);
-                    if (ray < a.R)
-                        a.out_rgb[ray * kRgb + 16 * h + (lane & 15)] = __fsub_rn(__fmul_rn(__fadd_rn(r[0], (lane >> 4) ? back[32 / RPT - 1] : back[0]), 2.f), 1.f);
-                }
-            }
-            tc_fence_before();
         };
         // tasks follow the pass schedule: importance(n) after C(n), merge(n) after F(n)
         Tick tr_(a.timing, blockIdx.x == 0 && rw == 0 && lane == 0);
@@ -868,21 +931,16 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             if (pd.pass == 0) {
                 mbar_wait(&sm.sigc_ready[si], par);
                 tr_.lap(13);                                                  // [13] wait for coarse sigma
-                for (int rl = rw * (GR / 4); rl < (rw + 1) * (GR / 4); ++rl) importance_ray(n, rl);   // the rays of TMEM lane quarter rw
-                __syncwarp();
+                for (int rl = rw; rl < GR; rl += kRW) importance_ray(n, rl);
                 if (lane == 0) mbar_arrive(&sm.fine_ready[si]);
                 tr_.lap(9);                                                   // [9] importance
             } else {
-                mbar_wait(&sm.sigf_ready[si], par);                           // all six tiles of group n are decoded (TMEM) and their sigma is in smem
-                tr_.lap(14);                                                  // [14] wait for fine sigma
-                float back[32 / RPT];
-#pragma unroll
-                for (int i = 0; i < 32 / RPT; ++i) back[i] = composite_ray(n, rw * (GR / 4) + i);   // omega / pos of a ray are private to its warp
+                mbar_wait(&sm.sigf_ready[si], par);
+                if (n >= 2) mbar_wait(&sm.state_free[(n - 2) & 3], ((n - 2) >> 2) & 1);       // colours(n-2) has released the omega slot
+                tr_.lap(14);                                                  // [14] wait for fine sigma / slot
+                for (int rl = rw; rl < GR; rl += kRW) composite_ray(n, rl);
+                if (lane == 0) mbar_arrive(&sm.omega_ready[n & 1]);
                 tr_.lap(10);                                                  // [10] merge / weights
-                colours_quarter(n, back);
-                __syncwarp();
-                if (lane == 0) { mbar_arrive(&sm.fa_free); mbar_arrive(&sm.state_free[si]); }
-                tr_.lap(11);                                                  // [11] colours
             }
         }
     } else {
@@ -895,9 +953,6 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
                 const int buf = it2 & 1;
                 mbar_wait(&sm.a2_full[buf], (it2 >> 1) & 1);
                 mbar_wait(&sm.dsig_empty, (it2 & 1) ^ 1);
-                // the shared fine area (and, later in the schedule, coarse area n % 3) is rewritten from here on: the ray warps
-                // must have finished the colour reduction of the previous fine pass
-                if (tp.pass == 1 && tp.k == 0 && tp.n >= 1) mbar_wait(&sm.fa_free, (tp.n - 1) & 1);
                 tc_fence_after();
                 const uint32_t a2h = smem_u32(sm.a2[buf][0]), a2l = smem_u32(sm.a2[buf][1]);
                 const uint32_t dc = tmem + d2_col(tp.n, tp.pass, tp.k), ds = tmem + kColSig;
@@ -972,7 +1027,7 @@ int render_forward_fused_ws3(const Geom& g, const p3d_render_params* p, const vo
                             const float* u_f, const Workspace& ws, float* out_rgb, float* out_depth, float* out_wsum,
                             float* out_xyz, cudaStream_t stream) {
     if (!fused_ws3_supported(g)) {
-        set_error("warp-specialised renderer supports depth_resolution == depth_resolution_importance in {48, 96} (got %d, %d)", g.S, g.Sf);
+        set_error("fused warp-specialised renderer supports depth_resolution == depth_resolution_importance in {48, 96} (got %d, %d)", g.S, g.Sf);
         return P3D_EUNSUPPORTED;
     }
     const long long R = (long long)g.N * g.M;
@@ -1023,7 +1078,7 @@ int render_forward_fused_ws3(const Geom& g, const p3d_render_params* p, const vo
         P3D_CUDA_TRY(cudaStreamSynchronize(stream));
         const int groups_cta0 = (a.n_groups + grid - 1) / grid;
         fprintf(stderr, "[p3d ws timing, CTA0, cycles/group over %d groups] G(warp0: 1/3 of tiles): wait_dep %.0f wait_ring %.0f gather %.0f | "
-                        "E(warp0): wait_d1 %.0f ld_d1 %.0f wait_a2 %.0f epi1 %.0f sigma %.0f R-colours %.0f other %.0f | "
+                        "E(warp0): wait_d1 %.0f ld_d1 %.0f wait_a2 %.0f epi1 %.0f sigma %.0f colours(+omega wait) %.0f other %.0f | "
                         "R(warp0): wait_sigc %.0f importance %.0f wait_sigf %.0f merge %.0f\n",
                 groups_cta0, (double)h[1] / groups_cta0, (double)h[2] / groups_cta0, (double)h[3] / groups_cta0, (double)h[5] / groups_cta0,
                 (double)h[6] / groups_cta0, (double)h[7] / groups_cta0, (double)h[8] / groups_cta0, (double)h[12] / groups_cta0,

@@ -57,14 +57,8 @@ int render_backward_v1(const Geom& g, const p3d_render_params* p, const void* pl
                        float* d_w2, float* d_b2, cudaStream_t stream);
 int launch_bounds_to_float(const unsigned int* bounds, float* out2, cudaStream_t stream);
 int launch_depth_finalize_f(float* depth, long long R, const float* bounds2, cudaStream_t stream);
-// fused: one persistent kernel, OSGDecoder on tcgen05 tensor cores (3-pass split bf16 or single-pass bf16).
-bool fused_supported(const Geom& g);
-int render_forward_fused(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
-                         const float* w2, const float* b2, const float* ro, const float* rd, const float* u_c,
-                         const float* u_f, const Workspace& ws, float* out_rgb, float* out_depth, float* out_wsum,
-                         float* out_xyz, cudaStream_t stream);
 // warp-specialised fused renderer (v3): 1 CTA/SM, gather / epilogue / ray / MMA roles, two ray groups in flight.
-// experimental pipeline-depth-3 variant (render_fused_ws3.cu): opt-in through P3D_FUSED_IMPL=v5, not validated on hardware yet
+// pipeline-depth-3 variant with dedicated ray warps (render_fused_ws3.cu): the default fused kernel (P3D_FUSED_IMPL=v3 selects the one above)
 bool fused_ws3_supported(const Geom& g);
 int render_forward_fused_ws3(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
                              const float* w2, const float* b2, const float* ro, const float* rd, const float* u_c,

@@ -52,12 +52,85 @@ def gather_views(local: torch.Tensor, n_views: int, dst: Optional[int] = None, g
     return torch.cat([o[:c] for o, c in zip(out, counts)]) if rank == dst else None
 
 
+class PeerGather:
+    """Rendered images -> the consumer rank, overlapped with the next render.
+
+    The NCCL gather is an SM kernel; the fused renderer is a persistent kernel that owns every SM (1 CTA/SM, 227 KB of
+    shared memory), so a collective launched beside it cannot start before the render ends - the exchange sits on the
+    critical path of every step.  Here the consumer rank exports ONE device buffer (`slots` x world x shard) through CUDA
+    IPC; every other rank maps it once and from then on delivers its shard with a peer-to-peer `copy_` on a side stream:
+    an NVLink DMA by the copy engines, no SM, no NCCL kernel, so it runs under the next step's render.  `fence()` makes
+    the consumer's view complete (side streams drained + one barrier); a consumer that streams results polls per slot.
+    Falls back to `gather_views` when the backend is not NCCL / the tensors are not CUDA (the CPU tests)."""
+
+    def __init__(self, shard_shape, dtype, device, dst: int = 0, group=None, slots: int = 2):
+        self.group, self.dst, self.slots = group, dst, slots
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.p2p = self.world > 1 and torch.device(device).type == 'cuda' and dist.get_backend(group) == 'nccl'
+        self.buf = self.remote = None
+        self.last = None
+        if not self.p2p:
+            return
+        from torch.multiprocessing.reductions import reduce_tensor
+        box = [None]
+        if self.rank == dst:
+            self.buf = torch.zeros((slots, self.world) + tuple(shard_shape), dtype=dtype, device=device)
+            box[0] = reduce_tensor(self.buf)                       # (rebuild_fn, args) carrying the cudaIpcMemHandle
+        dist.broadcast_object_list(box, src=dst, group=group)
+        if self.rank == dst:
+            self.remote = self.buf
+        else:
+            fn, fargs = box[0]
+            self.remote = fn(*fargs)                                # dst's memory mapped into this process (peer access over NVLink)
+        self.stream = torch.cuda.Stream(device=device)
+        dist.barrier(group=group)
+
+    def push(self, shard: torch.Tensor, step: int = 0):
+        """Deliver this rank's shard of step `step` (asynchronous; ordered after the work queued on the current stream)."""
+        if not self.p2p:
+            self.last = gather_views(shard, shard.shape[0] * self.world, self.dst, self.group)
+            return
+        cur = torch.cuda.current_stream(shard.device)
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self.remote[step % self.slots, self.rank].copy_(shard, non_blocking=True)
+        shard.record_stream(self.stream)
+
+    def join_current_stream(self):
+        """Make the current stream wait for the copies issued so far (so a CUDA-event bracket includes them)."""
+        if self.p2p:
+            torch.cuda.current_stream().wait_stream(self.stream)
+
+    def fence(self):
+        if self.p2p:
+            self.stream.synchronize()
+            dist.barrier(group=self.group)
+
+    def result(self, step: int = 0) -> Optional[torch.Tensor]:
+        """After fence(): the (world * shard_views, ...) tensor of step `step` on the consumer rank, None elsewhere."""
+        if not self.p2p:
+            return self.last
+        if self.rank != self.dst:
+            return None
+        b = self.buf[step % self.slots]
+        return b.reshape((b.shape[0] * b.shape[1],) + tuple(b.shape[2:]))
+
+
 def render_sharded(renderer, planes, decoder, ray_origins, ray_directions, options, dst: Optional[int] = 0, exact_depth: bool = True,
                    group=None, **flags):
     """Render this rank's slice of a batch that every rank holds the inputs of (e.g. 16 eval views of one subject)
-    and gather (rgb, depth, wsum, xyz) to `dst`.  planes with batch size 1 are shared by all views."""
+    and gather (rgb, depth, wsum, xyz) to `dst`.  planes with batch size 1 are shared by all views.
+    `exact_depth` makes the composite-depth clamp batch-wide.  'auto' ray limits (ray_start = ray_end = 'auto') carry a
+    second batch-wide reduction in the reference - rays that miss the box are given the min / max start of the whole
+    batch (renderer.py:167-170) - which is NOT exchanged here: it is taken over the shard, so such rays can differ from
+    the one-process render; the panic3d configurations use numeric limits."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world > 1 and options.get('ray_start') == 'auto' and options.get('ray_end') == 'auto':
+        import warnings
+        warnings.warn("render_sharded with 'auto' ray limits: the fill value of rays that miss the box is reduced per shard, not per "
+                      "batch (see the docstring)", RuntimeWarning, stacklevel=2)
     n = ray_origins.shape[0]
     a, b = shard_range(n, world, rank)
     pl = planes if planes.shape[0] == 1 and n != 1 else planes[a:b]

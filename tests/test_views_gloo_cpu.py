@@ -62,6 +62,14 @@ def _worker(rank, world, port, q):
         assert torch.equal(full[:, 0], torch.arange(n, dtype=torch.float32))
         only0 = views.gather_views(local, n, dst=0)
         assert (only0 is not None) == (rank == 0)
+        # PeerGather falls back to the collective gather off-GPU (on the box it is a CUDA-IPC peer copy): same result contract
+        pg = views.PeerGather((2, 3), torch.float32, 'cpu', dst=0)
+        pg.push(torch.full((2, 3), float(rank)), step=0)
+        pg.fence()
+        res = pg.result(0)
+        assert (res is not None) == (rank == 0)
+        if rank == 0:
+            assert res.shape == (2 * world, 3) and torch.equal(res[:, 0], torch.arange(world, dtype=torch.float32).repeat_interleave(2))
         # depth-bound protocol
         b2 = torch.tensor([1.0 + rank, 2.0 + rank])
         views.all_reduce_depth_bounds(b2)
