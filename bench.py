@@ -119,12 +119,8 @@ def _import_reference():
     src = os.path.join(REF_TREE, '_train', 'eg3dc', 'src')
     if not os.path.isdir(os.path.join(src, 'training', 'volumetric_rendering')):
         return None
-    import types
-    os.environ.setdefault('PROJECT_DN', REF_TREE)
-    for q in (src, REF_TREE):
-        if q not in sys.path:
-            sys.path.insert(0, q)
-    sys.modules.setdefault('kornia', types.ModuleType('kornia'))          # only paste_front / the loss use it
+    from baseline import ref_env
+    ref_env.setup()                                                       # PROJECT_DN, sys.path, kornia stub, plugin finder
     try:
         import training.triplane as ref_tp
         from training.volumetric_rendering.renderer import ImportanceRenderer

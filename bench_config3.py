@@ -105,17 +105,18 @@ def main():
         for key in ('image_raw', 'image', 'image_depth', 'image_weights', 'feature_image'):
             if key in a and key in b:
                 d = (a[key].float() - b[key].float()).abs()
-                rep[key] = {'max_abs': float(d.max()), 'mean_abs': float(d.mean()), 'shape': list(d.shape)}
+                rep[key] = {'max_abs': float(d.max()), 'mean_abs': float(d.mean()), 'frac_within_1e-3': float((d < 1e-3).float().mean()),
+                            'shape': list(d.shape)}
+        rep['note'] = ('cull_clouds = 0.5 is a hard threshold on sigma (renderer.py:150-153): a sample within rounding of it flips in one arm, '
+                       'so isolated rays differ by more than 1e-3 (same criterion as the cull fixtures in tests/test_render_gpu.py); the '
+                       '512^2 image goes through the fp16 super-resolution head')
         rep['views_per_s'] = {a['arm']: a['views_per_s'], b['arm']: b['views_per_s']}
         rep['speedup'] = b['views_per_s'] / a['views_per_s'] if a['arm'] == 'reference' else a['views_per_s'] / b['views_per_s']
         print(json.dumps(rep))
         return
-    if not os.path.isdir(os.path.join(REF_TREE, '_train', 'eg3dc', 'src', 'training')):
-        raise SystemExit('baseline/_ref is missing: run `bash baseline/install_ref.sh` in the build container')
-    os.environ['PROJECT_DN'] = REF_TREE
-    os.environ.setdefault('TORCH_EXTENSIONS_DIR', os.path.join(REF_TREE, '_torch_ext'))
-    sys.path[:0] = [ROOT, REF_TREE, os.path.join(REF_TREE, '_train', 'eg3dc', 'src')]
-    sys.modules.setdefault('kornia', types.ModuleType('kornia'))
+    sys.path.insert(0, ROOT)
+    from baseline import ref_env
+    ref_env.setup()
     dev = torch.device(args.device)
     if args.arm == 'ours':
         import panic3d_b200.dropin as dropin

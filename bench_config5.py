@@ -41,12 +41,9 @@ def main():
     ap.add_argument('--tiny', action='store_true', help='small channels (CPU smoke test of the harness)')
     ap.add_argument('--device', default='cuda:0')
     args = ap.parse_args()
-    if not os.path.isdir(os.path.join(REF_TREE, '_train', 'eg3dc', 'src', 'training')):
-        raise SystemExit('baseline/_ref is missing: run `bash baseline/install_ref.sh` in the build container')
-    os.environ['PROJECT_DN'] = REF_TREE
-    os.environ.setdefault('TORCH_EXTENSIONS_DIR', os.path.join(REF_TREE, '_torch_ext'))
-    sys.path[:0] = [ROOT, REF_TREE, os.path.join(REF_TREE, '_train', 'eg3dc', 'src')]
-    sys.modules.setdefault('kornia', types.ModuleType('kornia'))
+    sys.path.insert(0, ROOT)
+    from baseline import ref_env
+    ref_env.setup()
     import numpy as np
     import torch
     dev = torch.device(args.device)

@@ -57,9 +57,8 @@ def main():
                          "timed on the same GPU for the per-op comparison")
     args = ap.parse_args()
     if args.impl == 'reference':
-        ref = os.path.join(ROOT, 'baseline', '_ref')
-        os.environ.setdefault('TORCH_EXTENSIONS_DIR', os.path.join(ref, '_torch_ext'))
-        sys.path.insert(0, os.path.join(ref, '_train', 'eg3dc', 'src'))
+        from baseline import ref_env
+        ref_env.setup()
         from torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu
         assert 'baseline/_ref' in bias_act.__file__.replace(os.sep, '/')
     else:

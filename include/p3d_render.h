@@ -167,6 +167,11 @@ int p3d_decode_points(const p3d_render_params* p, const void* planes,
                       const float* coords, int64_t n_points_per_view,
                       float* out_rgb, float* out_sigma, void* stream);
 
+/* 1 when p3d_decode_points / p3d_volume_query have a tensor-core kernel for these params (mlp_mode P3D_MLP_TC_*: the
+   renderer's gather -> tcgen05 decoder pipeline streamed over the points; any point count), else 0 (fp32 SIMT kernels).
+   The host mirror's mlp_mode = 'auto' uses it like p3d_render_fused_supported. */
+int p3d_decode_tc_supported(const p3d_render_params* p, int64_t n_points_total);
+
 /* Backward of p3d_decode_points (first order): what the density-regularisation phase of the training loop needs
    (loss_orthocondA.py:579-600: G.sample_mixed(...)['sigma'] -> TVloss.backward(); triplane.py:283-298 -> run_model).
    Gradients flow to the tri-plane features and the four decoder tensors; the coordinates are constants (they carry

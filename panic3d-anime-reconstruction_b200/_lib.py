@@ -49,6 +49,7 @@ _PROTOS = {
     'p3d_raygen_ortho': (C.c_int, [_VP, _VP, C.c_int32, C.c_int32, C.c_double, _VP, _VP, _VP]),
     'p3d_render_workspace_bytes': (C.c_size_t, [C.POINTER(RenderParams)]),
     'p3d_render_fused_supported': (C.c_int, [C.POINTER(RenderParams)]),
+    'p3d_decode_tc_supported': (C.c_int, [C.POINTER(RenderParams), C.c_int64]),
     'p3d_render_forward': (C.c_int, [C.POINTER(RenderParams)] + [_VP] * 9 + [_VP, C.c_size_t] + [_VP] * 5),
     'p3d_decode_points': (C.c_int, [C.POINTER(RenderParams)] + [_VP] * 6 + [C.c_int64, _VP, _VP, _VP]),
     'p3d_decode_points_backward': (C.c_int, [C.POINTER(RenderParams)] + [_VP] * 6 + [C.c_int64] + [_VP] * 7 + [_VP]),

@@ -375,6 +375,12 @@ int p3d_render_fused_supported(const p3d_render_params* p) {
     return (fused_ws3_supported(g) || fused_ws_supported(g)) ? 1 : 0;
 }
 
+int p3d_decode_tc_supported(const p3d_render_params* p, int64_t n_points_total) {
+    Geom g;
+    if (!p || make_geom(p, &g)) return 0;
+    return decode_tc_supported(g, n_points_total) ? 1 : 0;
+}
+
 int p3d_render_forward(const p3d_render_params* p, const void* planes, const float* w1, const float* b1, const float* w2,
                        const float* b2, const float* ray_origins, const float* ray_dirs, const float* u_coarse,
                        const float* u_fine, void* workspace, size_t workspace_bytes, float* out_rgb, float* out_depth,
@@ -456,6 +462,13 @@ int p3d_decode_points(const p3d_render_params* p, const void* planes, const floa
     P3D_REQUIRE(n_points_per_view >= 0, "negative point count");
     if ((long long)g.N * n_points_per_view == 0) return P3D_OK;
     P3D_REQUIRE(planes && w1 && b1 && w2 && b2 && coords && out_rgb && out_sigma, "null pointer");
+    if (p->mlp_mode == P3D_MLP_TC_3XBF16 || p->mlp_mode == P3D_MLP_TC_BF16) {
+        if (!decode_tc_supported(g, (long long)g.N * n_points_per_view)) {
+            set_error("tensor-core point decode needs planes of at least 2x2 texels with non-negative strides below 2^31 elements per view");
+            return P3D_EUNSUPPORTED;
+        }
+        return decode_points_tc(g, p, planes, w1, b1, w2, b2, coords, n_points_per_view, out_rgb, out_sigma, (cudaStream_t)stream);
+    }
     return decode_points_v1(g, p, planes, w1, b1, w2, b2, coords, n_points_per_view, out_rgb, out_sigma, (cudaStream_t)stream);
 }
 
@@ -484,6 +497,14 @@ int p3d_volume_query(const p3d_render_params* p, const void* planes, const float
     P3D_REQUIRE(cube_length > 0, "cube_length must be > 0");
     if (g.N == 0) return P3D_OK;
     P3D_REQUIRE(planes && w1 && b1 && w2 && b2 && out_sigma, "null pointer");
+    if (p->mlp_mode == P3D_MLP_TC_3XBF16 || p->mlp_mode == P3D_MLP_TC_BF16) {
+        if (!decode_tc_supported(g, (long long)g.N * resolution * resolution * resolution)) {
+            set_error("tensor-core volume query needs planes of at least 2x2 texels with non-negative strides below 2^31 elements per view");
+            return P3D_EUNSUPPORTED;
+        }
+        return volume_query_tc(g, p, planes, w1, b1, w2, b2, resolution, cube_length, triplane_crop, cull_clouds, out_sigma, out_rgb,
+                               out_density, out_coords, (cudaStream_t)stream);
+    }
     return volume_query_v1(g, p, planes, w1, b1, w2, b2, resolution, cube_length, triplane_crop, cull_clouds, out_sigma,
                            out_rgb, out_density, out_coords, (cudaStream_t)stream);
 }

@@ -22,13 +22,14 @@
 //                          omega and the per-ray outputs after its fine pass
 //   warp  24     MMA       one thread: layer-1 and layer-2 tcgen05.mma, commits
 #include <stdlib.h>
-#include "render_device.cuh"
+#include "fused_common.cuh"
 
 namespace p3d {
 
 namespace {
 
 using namespace dev;
+using namespace fused;
 
 constexpr int kGW = 12, kEW = 8, kRW = 4, kTeams = 3;   // 25 warps: 7 on one SM sub-partition -> 72 registers per thread
 constexpr int kWarpsWS = kGW + kEW + kRW + 1;
@@ -40,12 +41,8 @@ constexpr int kTmemColsWS = 512;
 constexpr int kColD1 = 0, kColSig = 64, kColCA = 96, kColFA = 384;   // see the TMEM map above
 __device__ __forceinline__ uint32_t d2_col(int n, int pass, int k) { return (uint32_t)(pass == 0 ? kColCA + (n % 3) * 96 + k * 32 : kColFA + k * 32); }
 
-constexpr int kSBO = 128, kLBO_A = 2048, kLBO_A1 = 2080, kLBO_W1 = 1024, kLBO_W2C = 512, kLBO_W2S = 256;
-constexpr bool kG256 = false;
+constexpr int kLBO_A = 2048, kLBO_A1 = 2080, kLBO_W1 = 1024, kLBO_W2C = 512, kLBO_W2S = 256;
 // build-time A/B switches (profiles/r2_kernel_log.md); the defaults are what ships
-#ifndef P3D_W3_WAIT
-#define P3D_W3_WAIT 0          // 0: try_wait with a suspend-time hint, bounded (traps on a protocol bug); 2: plain try_wait, bounded (measured slower)
-#endif
 #ifndef P3D_W3_LG2POLY
 #define P3D_W3_LG2POLY 0       // 1: the lg2(1 + t) half of the tile epilogue's softplus as a packed polynomial on the FMA pipe (needs P3D_W3_SOFTPLUS)
 #endif
@@ -53,7 +50,6 @@ constexpr bool kG256 = false;
 #define P3D_W3_SOFTPLUS 1      // 1: guard-free softplus max(x,0) + lg2(1 + 2^-|x|) with packed f32x2 adds and a packed hi/lo split
 #endif
 
-constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
 struct GroupState {                               // written by G (t_c, crop), E (sg_*), R (t_f)
     float t_c[kRowsG], sg_c[kRowsG], t_f[kRowsG], sg_f[kRowsG];
@@ -103,202 +99,6 @@ struct Tick {
     __device__ Tick(unsigned long long* d, bool enable) : dst(d), t0(0), on(enable && d != nullptr) { if (on) t0 = clock64(); }
     __device__ void lap(int slot) { if (on) { const long long t1 = clock64(); atomicAdd(dst + slot, (unsigned long long)(t1 - t0)); t0 = t1; } }
 };
-
-// ------------------------------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-#if P3D_W3_WAIT == 2
-#pragma unroll 1
-    for (int it = 0; it < (1 << 24); ++it) {             // plain try_wait: the hardware's own suspend window per try; still bounded
-        uint32_t ok;
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-        if (ok) return;
-    }
-    asm volatile("trap;");
-#endif
-    // (not unrolled: ptxas otherwise replicates the body 16x at each of the ~50 call sites - half of the kernel's code size)
-#pragma unroll 1
-    for (int it = 0; it < (1 << 17); ++it) {             // ~20 us per try: the cap turns a protocol bug into a trap after ~2 s
-        uint32_t ok;
-        // the suspend-time hint lets a waiting warp sleep in hardware instead of polling: roles that run ahead of the
-        // critical path must not steal issue slots from it
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(addr), "r"(parity), "r"(20000u) : "memory");
-        if (ok) return;
-    }
-    asm volatile("trap;");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    uint64_t d = (uint64_t)((saddr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
-    d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
-    d |= 1ull << 46;
-    return d;
-}
-__device__ __forceinline__ constexpr uint32_t umma_idesc(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n\t"
-        "tcgen05.wait::ld.sync.aligned;"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr) : "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-__device__ __forceinline__ float tmem_ld1(uint32_t taddr) {
-    uint32_t r;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];\n\ttcgen05.wait::ld.sync.aligned;" : "=r"(r) : "r"(taddr) : "memory");
-    return __uint_as_float(r);
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float e0, float e1) {
-    uint32_t d;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(e1), "f"(e0));
-    return d;
-}
-__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-    hi = pack_bf16x2(a, b);
-    lo = pack_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
-}
-__device__ __forceinline__ void split1(float x, unsigned short& hi, unsigned short& lo) {
-    const __nv_bfloat16 h = __float2bfloat16_rn(x);
-    hi = __bfloat16_as_ushort(h);
-    lo = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
-}
-__device__ __forceinline__ int tile_off(int row, int k, int lbo) { return (row >> 3) * kSBO + (k >> 3) * lbo + (row & 7) * 16 + (k & 7) * 2; }
-
-// ------------------------------------------------------------------------------------------ gather
-// Tap table: one 64 B record per row - chunk 0 = {o[0], o[1], o[2], flags}, chunk 1+p = the four bilinear weights of plane p
-// (w00, w01, w10, w11; rows y, y+1 x columns x, x+1) - chunk c of row r stored at position c ^ ((r >> 1) & 3), which makes
-// both the lane = row writes and the 8-rows-per-phase reads of the gather conflict-free.  o[p] is the element offset of texel
-// (ya, xa) of plane p inside the view's tri-plane, with (ya, xa) CLAMPED to [0, H-2] x [0, W-2]: the 2 x 2 footprint that is
-// loaded is always inside the plane, and the weights are moved onto the loaded texels (grid_sample's zero padding,
-// renderer.py:68-81: a tap outside the plane contributes nothing, so its weight is dropped; a footprint that hangs over the
-// edge by one texel keeps the weights of its inside texels).  flags bit p = plane p has a non-zero weight; the loads of a
-// plane whose bit is clear are predicated off (its registers keep older, finite texel values that meet weights of 0).
-__device__ __forceinline__ uint32_t tab_off(int row, int chunk) { return (uint32_t)(row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4)); }
-
-__device__ __forceinline__ bool plane_taps_rec(const Geom& g, const WsArgs& a, int pbase, float ca, float cb, uint32_t& o, float4& w) {
-    const float gx = __fmul_rn(ca, g.coord_scale), gy = __fmul_rn(cb, g.coord_scale);
-    const float fx = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)g.W), 1.f), 0.5f);
-    const float fy = __fmul_rn(__fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)g.H), 1.f), 0.5f);
-    const bool sane = (fx > -2.f) && (fx < (float)g.W + 1.f) && (fy > -2.f) && (fy < (float)g.H + 1.f);   // false for NaN too
-    const float x0f = floorf(fx), y0f = floorf(fy);
-    const float wx1 = fx - x0f, wy1 = fy - y0f;
-    const float wx0 = 1.f - wx1, wy0 = 1.f - wy1;
-    const int x0 = sane ? (int)x0f : -4, y0 = sane ? (int)y0f : -4;
-    const int xa = min(max(x0, 0), g.W - 2), ya = min(max(y0, 0), g.H - 2);
-    const int dx = x0 - xa, dy = y0 - ya;                     // 0 inside, -1 / +1: the footprint hangs over the low / high edge
-    const float wl = dx == 0 ? wx0 : (dx == -1 ? wx1 : 0.f), wr = dx == 0 ? wx1 : (dx == 1 ? wx0 : 0.f);
-    const float wt = dy == 0 ? wy0 : (dy == -1 ? wy1 : 0.f), wb = dy == 0 ? wy1 : (dy == 1 ? wy0 : 0.f);
-    o = (uint32_t)(pbase + ya * a.srow + xa * a.scol);
-    w = make_float4(wl * wt, wr * wt, wl * wb, wr * wb);
-    return ((unsigned)(dx + 1) < 3u) && ((unsigned)(dy + 1) < 3u);
-}
-// eight consecutive channels of one texel (32 B fp32 / 16 B bf16) at addr + IMM bytes, predicated; v keeps its old value when !pred
-template <bool BF16, int IMM>
-__device__ __forceinline__ void load_oct(float (&v)[8], const char* addr, bool pred) {
-    if (BF16) {
-        uint32_t r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4+%6];\n\t}"
-                     : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3) : "l"(addr), "r"((int)pred), "n"(IMM));
-        if (pred) {
-            v[0] = __uint_as_float(r0 << 16); v[1] = __uint_as_float(r0 & 0xffff0000u); v[2] = __uint_as_float(r1 << 16); v[3] = __uint_as_float(r1 & 0xffff0000u);
-            v[4] = __uint_as_float(r2 << 16); v[5] = __uint_as_float(r2 & 0xffff0000u); v[6] = __uint_as_float(r3 << 16); v[7] = __uint_as_float(r3 & 0xffff0000u);
-        }
-    } else {
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %9, 0;\n\t@p ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8+%10];\n\t}"
-                     : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7])
-                     : "l"(addr), "r"((int)pred), "n"(IMM));
-    }
-}
-// packed f32x2 arithmetic (one instruction for two lanes of data)
-__device__ __forceinline__ unsigned long long pk2(float a, float b) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
-__device__ __forceinline__ void upk2(unsigned long long v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
-__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
-__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-// lg2(1 + t) for t in [0, 1] on the FMA pipe, two values per instruction: t * q(t), q = degree-6 near-minimax fit of
-// lg2(1 + t) / t (max abs error 1.4e-6 in fp32 Horner form, exact 0 at t = 0).  Takes the second MUFU of every softplus off the
-// MUFU / MIO queue, which is what throttles the tile epilogue (ncu: mio_throttle on the softplus lines).
-__device__ __forceinline__ unsigned long long lg2_1p_poly2(unsigned long long t) {
-    unsigned long long q = fma2(t, pk2(0.020490340888500214f, 0.020490340888500214f), pk2(-0.09606623649597168f, -0.09606623649597168f));
-    q = fma2(t, q, pk2(0.2155885100364685f, 0.2155885100364685f));
-    q = fma2(t, q, pk2(-0.33924776315689087f, -0.33924776315689087f));
-    q = fma2(t, q, pk2(0.4777059257030487f, 0.4777059257030487f));
-    q = fma2(t, q, pk2(-0.721162736415863f, -0.721162736415863f));
-    q = fma2(t, q, pk2(1.4426932334899902f, 1.4426932334899902f));
-    return mul2(t, q);
-}
-// (h0, h1) -> bf16x2 hi word and bf16x2 lo word of the residuals, 4 instructions + the pack
-__device__ __forceinline__ void split2p(unsigned long long h2, uint32_t& hi, uint32_t& lo) {
-    float h0, h1;
-    upk2(h2, h0, h1);
-    hi = pack_bf16x2(h0, h1);
-    const unsigned long long r2 = sub2(h2, pk2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xffff0000u)));
-    float r0, r1;
-    upk2(r2, r0, r1);
-    lo = pack_bf16x2(r0, r1);
-}
-// four consecutive channels of one texel (16 B fp32 / 8 B bf16) at addr + IMM bytes, predicated; v keeps its old value when !pred
-template <bool BF16, int IMM>
-__device__ __forceinline__ void load_quad_p(float (&v)[4], const char* addr, bool pred) {
-    if (BF16) {
-        uint32_t r0 = 0, r1 = 0;
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %3, 0;\n\t@p ld.global.nc.v2.u32 {%0,%1}, [%2+%4];\n\t}"
-                     : "+r"(r0), "+r"(r1) : "l"(addr), "r"((int)pred), "n"(IMM));
-        v[0] = __uint_as_float(r0 << 16); v[1] = __uint_as_float(r0 & 0xffff0000u); v[2] = __uint_as_float(r1 << 16); v[3] = __uint_as_float(r1 & 0xffff0000u);   // zeros when !pred
-    } else {
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4+%6];\n\t}"
-                     : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]) : "l"(addr), "r"((int)pred), "n"(IMM));
-    }
-}
-__device__ __forceinline__ void fma4(unsigned long long (&acc)[2], const float (&v)[4], float w) {
-    unsigned long long ww;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        unsigned long long vv;
-        asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "f"(v[2 * j]), "f"(v[2 * j + 1]));
-        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j]) : "l"(vv), "l"(ww));
-    }
-}
-// acc[0..8) += v[0..8) * w as four packed FFMA2 (the scalar weight is broadcast by the instruction)
-__device__ __forceinline__ void fma8(unsigned long long (&acc)[4], const float (&v)[8], float w) {
-    unsigned long long ww;
-    asm("mov.b64 %0, {%1, %1};" : "=l"(ww) : "f"(w));
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        unsigned long long vv;
-        asm("mov.b64 %0, {%1, %2};" : "=l"(vv) : "f"(v[2 * j]), "f"(v[2 * j + 1]));
-        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[j]) : "l"(vv), "l"(ww));
-    }
-}
 
 // pass j of a CTA with N groups:  C(0) C(1) | F(0) C(2) | F(1) C(3) | ... | F(N-2) F(N-1)   (N == 1: C(0) F(0))
 struct PassDesc { int n, pass; };
@@ -388,7 +188,6 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
         constexpr int kImmX = SCOL * kEsz;                                  // byte offset of the x+1 texel when the column stride is static
         const long long scolB = (long long)a.scol * kEsz, srowB = (long long)a.srow * kEsz;
         unsigned char* tab = reinterpret_cast<unsigned char*>(sm.tab[gw]);
-        const int q8 = lane >> 3, rr = lane & 7;                            // gather lane = (channel octet q8, row rr of the round)
         float v[6][8];
 #pragma unroll
         for (int k = 0; k < 6; ++k)
@@ -442,9 +241,9 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
                 const bool pm = g.plane_mode == P3D_PLANES_PANIC3D;
                 uint32_t o0, o1, o2;
                 float4 w0, w1, w2;
-                const bool f0 = plane_taps_rec(g, a, 0, px, py, o0, w0);
-                const bool f1 = plane_taps_rec(g, a, a.splane, px, pz, o1, w1);
-                const bool f2 = plane_taps_rec(g, a, 2 * a.splane, pm ? py : pz, pm ? pz : px, o2, w2);
+                const bool f0 = plane_taps_rec(g, a.srow, a.scol, 0, px, py, o0, w0);
+                const bool f1 = plane_taps_rec(g, a.srow, a.scol, a.splane, px, pz, o1, w1);
+                const bool f2 = plane_taps_rec(g, a.srow, a.scol, 2 * a.splane, pm ? py : pz, pm ? pz : px, o2, w2);
                 *reinterpret_cast<uint4*>(tab + tab_off(lane, 0)) = make_uint4(o0, o1, o2, (f0 ? 1u : 0u) | (f1 ? 2u : 0u) | (f2 ? 4u : 0u));
                 *reinterpret_cast<float4*>(tab + tab_off(lane, 1)) = w0;
                 *reinterpret_cast<float4*>(tab + tab_off(lane, 2)) = w1;
@@ -457,7 +256,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             tk_.lap(2);                                                   // [2] taps + wait a1_empty
             unsigned char* a1h = sm.a1[stage][0];
             unsigned char* a1l = sm.a1[stage][1];
-            if constexpr (!kG256) {
+            {
                 // ---- gather: 8 rounds of 4 rows; lane (sub, qd) loads channels [4 qd, 4 qd + 4) of the 12 taps of row 4 round + sub:
                 //      twelve 128-bit loads in flight per lane, each warp-wide load covers four whole 128 B texels (one L1
                 //      wavefront per texel)
@@ -503,53 +302,6 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
                     *reinterpret_cast<uint2*>(a1h + off) = make_uint2(h[0], h[1]);
                     *reinterpret_cast<uint2*>(a1l + off) = make_uint2(l[0], l[1]);
                 }
-            } else {
-            const char* vq = reinterpret_cast<const char*>(a.planes) + ((long long)view * g.stride_view + 8 * q8) * kEsz;
-            // ---- gather: 4 rounds of 8 rows; lane (q8, rr) loads channels [8 q8, 8 q8 + 8) of the 12 taps of row 8 round + rr in
-            //      two halves of six 256-bit loads (plane 0 + the upper texel row of plane 1 | the lower row of plane 1 + plane 2)
-#pragma unroll 1
-            for (int round = 0; round < 4; ++round) {
-                const int lrow = round * 8 + rr;
-                const uint4 c0 = *reinterpret_cast<const uint4*>(tab + tab_off(lrow, 0));
-                const bool p0 = c0.w & 1u, p1 = c0.w & 2u, p2 = c0.w & 4u;
-                const char* b0 = vq + (unsigned long long)c0.x * kEsz;
-                const char* b1 = vq + (unsigned long long)c0.y * kEsz;
-                const char* b2 = vq + (unsigned long long)c0.z * kEsz;
-                // half 1
-                load_oct<BF16, 0>(v[0], b0, p0);
-                if (SCOL) load_oct<BF16, kImmX>(v[1], b0, p0); else load_oct<BF16, 0>(v[1], b0 + scolB, p0);
-                load_oct<BF16, 0>(v[2], b0 + srowB, p0);
-                if (SCOL) load_oct<BF16, kImmX>(v[3], b0 + srowB, p0); else load_oct<BF16, 0>(v[3], b0 + srowB + scolB, p0);
-                load_oct<BF16, 0>(v[4], b1, p1);
-                if (SCOL) load_oct<BF16, kImmX>(v[5], b1, p1); else load_oct<BF16, 0>(v[5], b1 + scolB, p1);
-                unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
-                const float4 w0 = *reinterpret_cast<const float4*>(tab + tab_off(lrow, 1));
-                const float4 w1 = *reinterpret_cast<const float4*>(tab + tab_off(lrow, 2));
-                fma8(acc, v[0], w0.x); fma8(acc, v[1], w0.y); fma8(acc, v[2], w0.z); fma8(acc, v[3], w0.w);
-                fma8(acc, v[4], w1.x); fma8(acc, v[5], w1.y);
-                // half 2
-                load_oct<BF16, 0>(v[0], b1 + srowB, p1);
-                if (SCOL) load_oct<BF16, kImmX>(v[1], b1 + srowB, p1); else load_oct<BF16, 0>(v[1], b1 + srowB + scolB, p1);
-                load_oct<BF16, 0>(v[2], b2, p2);
-                if (SCOL) load_oct<BF16, kImmX>(v[3], b2, p2); else load_oct<BF16, 0>(v[3], b2 + scolB, p2);
-                load_oct<BF16, 0>(v[4], b2 + srowB, p2);
-                if (SCOL) load_oct<BF16, kImmX>(v[5], b2 + srowB, p2); else load_oct<BF16, 0>(v[5], b2 + srowB + scolB, p2);
-                const float4 w2 = *reinterpret_cast<const float4*>(tab + tab_off(lrow, 3));
-                fma8(acc, v[0], w1.z); fma8(acc, v[1], w1.w);
-                fma8(acc, v[2], w2.x); fma8(acc, v[3], w2.y); fma8(acc, v[4], w2.z); fma8(acc, v[5], w2.w);
-                // mean over the planes (the 1/3 is folded into W1), bf16 hi/lo split, one 16 B K-chunk each
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float e0, e1;
-                    asm("mov.b64 {%0, %1}, %2;" : "=f"(e0), "=f"(e1) : "l"(acc[j]));
-                    split2(e0, e1, h[j], l[j]);
-                }
-                const int trow = wt * 32 + lrow;
-                const int off = (trow >> 3) * kSBO + q8 * kLBO_A1 + (trow & 7) * 16;
-                *reinterpret_cast<uint4*>(a1h + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4*>(a1l + off) = make_uint4(l[0], l[1], l[2], l[3]);
-            }
             }
             fence_proxy_async();
             __syncwarp();                                                   // also: the tap table is rewritten by the next tile

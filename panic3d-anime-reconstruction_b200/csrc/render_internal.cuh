@@ -72,6 +72,14 @@ int render_forward_fused_ws(const Geom& g, const p3d_render_params* p, const voi
 int decode_points_v1(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
                      const float* w2, const float* b2, const float* coords, long long n_pts, float* out_rgb,
                      float* out_sigma, cudaStream_t stream);
+// streaming tensor-core decode (decode_tc.cu): the gather -> tcgen05 decoder pipeline of the renderer without per-ray phases
+bool decode_tc_supported(const Geom& g, long long total);
+int decode_points_tc(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
+                     const float* w2, const float* b2, const float* coords, long long n_pts, float* out_rgb,
+                     float* out_sigma, cudaStream_t stream);
+int volume_query_tc(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
+                    const float* w2, const float* b2, int res, double cube_length, double triplane_crop, double cull_clouds,
+                    float* out_sigma, float* out_rgb, float* out_density, float* out_coords, cudaStream_t stream);
 int decode_points_backward_v1(const Geom& g, const p3d_render_params* p, const void* planes, const float* w1, const float* b1,
                               const float* w2, const float* b2, const float* coords, long long n_pts, const float* g_rgb,
                               const float* g_sigma, float* d_planes, float* d_w1, float* d_b1, float* d_w2, float* d_b2,

@@ -207,7 +207,7 @@ class ImportanceRenderer(torch.nn.Module):
         self._workspace = None
 
     # ------------------------------------------------------------------ helpers
-    def _params(self, planes_cl, N, M, opts, decoder, triplane_crop, cull_clouds, binarize_clouds):
+    def _params(self, planes_cl, N, M, opts, decoder, triplane_crop, cull_clouds, binarize_clouds, n_points=None):
         if int(opts.get('triplane_depth', 1)) != 1:
             raise NotImplementedError('triplane_depth > 1 (multiplane) is outside the accelerated path')
         if opts.get('density_noise', 0) > 0:
@@ -242,7 +242,9 @@ class ImportanceRenderer(torch.nn.Module):
         p.force_sigmoid = 1 if force_sigmoid else 0
         if self.mlp_mode == 'auto':
             p.mlp_mode = _lib.P3D_MLP_TC_3XBF16
-            if not _lib.lib().p3d_render_fused_supported(C.byref(p)):
+            ok = (_lib.lib().p3d_render_fused_supported(C.byref(p)) if n_points is None      # ray rendering
+                  else _lib.lib().p3d_decode_tc_supported(C.byref(p), int(n_points)))       # point / volume decode
+            if not ok:
                 p.mlp_mode = _lib.P3D_MLP_FP32_SIMT
         else:
             p.mlp_mode = int(self.mlp_mode)
@@ -367,7 +369,7 @@ class ImportanceRenderer(torch.nn.Module):
             planes_cl = self._planes_cl(planes.detach())
             opts = dict(options)
             opts.setdefault('depth_resolution', 2)
-            p, (w1, b1, w2, b2) = self._params(planes_cl, N, 0, opts, decoder, None, None, None)
+            p, (w1, b1, w2, b2) = self._params(planes_cl, N, 0, opts, decoder, None, None, None, n_points=N * K)
             coords = sample_coordinates.detach().float().contiguous()
             rgb = torch.empty((N, K, p.out_dim - 1), device=dev, dtype=torch.float32)
             sigma = torch.empty((N, K, 1), device=dev, dtype=torch.float32)

@@ -63,7 +63,7 @@ def query_volume(planes, decoder, rendering_kwargs, resolution=256, triplane_cro
         planes_cl = r._planes_cl(planes.detach())
         opts = dict(rendering_kwargs)
         opts.setdefault('depth_resolution', 2)
-        p, wts = r._params(planes_cl, N, 0, opts, decoder, None, None, None)
+        p, wts = r._params(planes_cl, N, 0, opts, decoder, None, None, None, n_points=N * int(resolution) ** 3)
         wt = [t.detach().float().contiguous() for t in wts]
         sig = torch.empty((N, R, R, R, 1), device=dev, dtype=torch.float32)
         dens = torch.empty((N, R, R, R, 1), device=dev, dtype=torch.float32)
