@@ -214,6 +214,20 @@ int p3d_render_forward_host(const p3d_render_params* p, const float* planes_nchw
                             float* out_rgb, float* out_depth, float* out_wsum, float* out_xyz);
 void p3d_host_arena_release(void);
 
+/* Peer-to-peer delivery of rendered images between the per-GPU processes of one box (views.PeerGather): the consumer rank
+   allocates a device buffer and exports it; every other rank opens the handle ON ITS OWN device (peer access over NVLink is
+   enabled lazily by the driver) and copies its shard into it with the copy engines - no SM, so the transfer runs under the
+   persistent renderer of the next step, which an NCCL kernel cannot.
+     p3d_ipc_alloc   cudaMalloc + cudaIpcGetMemHandle; handle64 receives the 64-byte cudaIpcMemHandle_t
+     p3d_ipc_open    cudaIpcOpenMemHandle(cudaIpcMemLazyEnablePeerAccess) on the current device
+     p3d_ipc_close / p3d_ipc_free   undo the above
+     p3d_copy_async  cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, stream) */
+int p3d_ipc_alloc(size_t bytes, void** dptr, unsigned char* handle64);
+int p3d_ipc_open(const unsigned char* handle64, void** dptr);
+int p3d_ipc_close(void* dptr);
+int p3d_ipc_free(void* dptr);
+int p3d_copy_async(void* dst, const void* src, size_t bytes, void* stream);
+
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t p3d_launch_count(void);
 

@@ -60,6 +60,11 @@ _PROTOS = {
     'p3d_render_depth_bounds': (C.c_int, [_VP, _VP, _VP]),
     'p3d_depth_finalize': (C.c_int, [_VP, C.c_int64, _VP, _VP]),
     'p3d_host_arena_release': (None, []),
+    'p3d_ipc_alloc': (C.c_int, [C.c_size_t, C.POINTER(_VP), C.c_char_p]),
+    'p3d_ipc_open': (C.c_int, [C.c_char_p, C.POINTER(_VP)]),
+    'p3d_ipc_close': (C.c_int, [_VP]),
+    'p3d_ipc_free': (C.c_int, [_VP]),
+    'p3d_copy_async': (C.c_int, [_VP, _VP, C.c_size_t, _VP]),
     'p3d_profile_enable': (None, [C.c_int]),
     'p3d_profile_read': (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int, C.c_int]),
 }

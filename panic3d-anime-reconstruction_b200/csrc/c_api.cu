@@ -610,6 +610,41 @@ int p3d_render_forward_host(const p3d_render_params* p_in, const float* planes_n
     return P3D_OK;
 }
 
+int p3d_ipc_alloc(size_t bytes, void** dptr, unsigned char* handle64) {
+    P3D_REQUIRE(dptr && handle64 && bytes > 0, "bad arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    P3D_CUDA_TRY(cudaMalloc(dptr, bytes));
+    P3D_CUDA_TRY(cudaMemset(*dptr, 0, bytes));
+    cudaIpcMemHandle_t h;
+    P3D_CUDA_TRY(cudaIpcGetMemHandle(&h, *dptr));
+    memcpy(handle64, &h, 64);
+    return P3D_OK;
+}
+
+int p3d_ipc_open(const unsigned char* handle64, void** dptr) {
+    P3D_REQUIRE(dptr && handle64, "bad arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    P3D_CUDA_TRY(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return P3D_OK;
+}
+
+int p3d_ipc_close(void* dptr) {
+    if (dptr) P3D_CUDA_TRY(cudaIpcCloseMemHandle(dptr));
+    return P3D_OK;
+}
+
+int p3d_ipc_free(void* dptr) {
+    if (dptr) P3D_CUDA_TRY(cudaFree(dptr));
+    return P3D_OK;
+}
+
+int p3d_copy_async(void* dst, const void* src, size_t bytes, void* stream) {
+    P3D_REQUIRE(dst && src, "null pointer");
+    P3D_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return P3D_OK;
+}
+
 void p3d_host_arena_release(void) {
     std::lock_guard<std::mutex> lock(g_arena.mu);
     g_arena.release();

@@ -368,9 +368,10 @@ int launch_decode(const Geom& g, const p3d_render_params* p, DecArgs& a, cudaStr
     a.single_pass = p->mlp_mode == P3D_MLP_TC_BF16;
     a.srow = (int)g.stride_row; a.scol = (int)g.stride_col; a.splane = (int)g.stride_plane;
     a.n_tiles = (int)((a.total + 127) / 128);
-    const bool sc32 = g.stride_col == kC;
-    void (*kern)(DecArgs) = p->planes_bf16 ? (sc32 ? k_decode_tc<true, VOLUME, kC> : k_decode_tc<true, VOLUME, 0>)
-                                           : (sc32 ? k_decode_tc<false, VOLUME, kC> : k_decode_tc<false, VOLUME, 0>);
+    const int sc = g.stride_col == kC ? 1 : (g.stride_col == 3 * kC ? 2 : 0);      // static texel stride: layout pre-pass / zero-copy channels_last
+#define P3D_PICK(BF) (sc == 1 ? k_decode_tc<BF, VOLUME, kC> : (sc == 2 ? k_decode_tc<BF, VOLUME, 3 * kC> : k_decode_tc<BF, VOLUME, 0>))
+    void (*kern)(DecArgs) = p->planes_bf16 ? P3D_PICK(true) : P3D_PICK(false);
+#undef P3D_PICK
     const size_t smem = sizeof(DecSmem) + 1024;
     P3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = a.n_tiles < n_sm ? a.n_tiles : n_sm;

@@ -43,6 +43,9 @@ __device__ __forceinline__ uint32_t d2_col(int n, int pass, int k) { return (uin
 
 constexpr int kLBO_A = 2048, kLBO_A1 = 2080, kLBO_W1 = 1024, kLBO_W2C = 512, kLBO_W2S = 256;
 // build-time A/B switches (profiles/r2_kernel_log.md); the defaults are what ships
+#ifndef P3D_W3_GCOL
+#define P3D_W3_GCOL 1          // 1: the colour reduction out of TMEM is shared by the twelve GATHER warps (which wait ~1/3 of the time on the A1
+#endif                         //    ring) and finalised by the ray warps, instead of stalling the epilogue role once per group
 #ifndef P3D_W3_LG2POLY
 #define P3D_W3_LG2POLY 0       // 1: the lg2(1 + t) half of the tile epilogue's softplus as a packed polynomial on the FMA pipe (needs P3D_W3_SOFTPLUS)
 #endif
@@ -61,6 +64,7 @@ struct SlotState {                                // written by R (composite), r
     float acc[8][kRgb];
     float back[8];
 };
+constexpr bool kGCol = P3D_W3_GCOL != 0;
 
 struct __align__(1024) WsSmem {
     unsigned char a1[kNA][2][4 * kLBO_A1];
@@ -74,7 +78,9 @@ struct __align__(1024) WsSmem {
     unsigned long long a1_full[kNA], a1_empty[kNA], a2_full[2], a2_empty[2];
     unsigned long long d1_full, d1_empty, d2_full, dsig_empty;
     unsigned long long fine_ready[kStates], state_free[kStates];
-    unsigned long long sigc_ready[kStates], sigf_ready[kStates], omega_ready[2];   // E -> R (sigma in smem), R -> E (omega)
+    unsigned long long sigc_ready[kStates], sigf_ready[kStates], omega_ready[2];   // E -> R (sigma in smem), R -> E / G (omega)
+    unsigned long long fa_free;                                    // GCOL: G -> MMA, R: the colour shares of a group have left TMEM
+    float part[kTeams][8][kRgb];                                   // GCOL: per-team partial colour sums of the group being reduced
     unsigned int tmem_base, pad1;
 };
 
@@ -141,10 +147,11 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
         for (int i = 0; i < 2; ++i) { mbar_init(&sm.a2_full[i], kEW); mbar_init(&sm.a2_empty[i], 1); }
         mbar_init(&sm.d1_full, 1); mbar_init(&sm.d1_empty, kEW); mbar_init(&sm.d2_full, 1); mbar_init(&sm.dsig_empty, 4);
         for (int i = 0; i < kStates; ++i) {
-            mbar_init(&sm.fine_ready[i], kRW); mbar_init(&sm.state_free[i], 1);
+            mbar_init(&sm.fine_ready[i], kRW); mbar_init(&sm.state_free[i], kGCol ? kRW : 1);
             mbar_init(&sm.sigc_ready[i], 4); mbar_init(&sm.sigf_ready[i], 4);      // the four chunk-0 epilogue warps
         }
         mbar_init(&sm.omega_ready[0], kRW); mbar_init(&sm.omega_ready[1], kRW);
+        mbar_init(&sm.fa_free, kGW);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = tid; i < kHidden * kC; i += kThreadsWS) {            // W1' = W1 * gain * log2(e)   (64 x 32)
@@ -193,6 +200,61 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
         for (int k = 0; k < 6; ++k)
 #pragma unroll
             for (int c = 0; c < 8; ++c) v[k][c] = 0.f;
+        // GCOL: this warp's share of the colour reduction of group n - sum_j omega_j c_j over the six parked tiles, straight out
+        // of TMEM.  Team j takes tiles 2j and 2j+1; warp wt reads its own TMEM lane quarter (= its ray at S = 96, its two rays
+        // at S = 48); the per-team partial sums go to sm.part and are added up in a fixed order by the ray warps, so the result
+        // is bit-reproducible.  The gather warps wait about a third of the time on the A1 ring: this fills that time instead of
+        // stalling the epilogue role once per group.
+        const uint32_t lane_base_g = (uint32_t)(wt * 32) << 16;
+        auto colour_share = [&](int n) {
+            SlotState& sl = sm.slot[n & 1];
+            mbar_wait(&sm.omega_ready[n & 1], (n >> 1) & 1);               // omega / pos of group n (ray warps)
+            tc_fence_after();
+            const int grp = (int)blockIdx.x + n * (int)gridDim.x;
+            const long long ray0 = (long long)grp * GR;
+            float part[2] = {0.f, 0.f};
+            const int rl_first = (wt * 32) / RPT;
+            for (int i = 0; i < 2; ++i) {
+                const int tile6 = 2 * team + i;
+                const int pass = tile6 / 3, k = tile6 - pass * 3;
+                const int trow = wt * 32 + lane;
+                const int rl = trow / RPT, s = k * RPT + (trow - rl * RPT);
+                const bool live = ray0 + rl < a.R;
+                const float om = live ? sl.om[rl * L + sl.pos[pass * kRowsG + rl * S + s]] : 0.f;
+                const float ca = g.force_sigmoid ? om : 1.002f * om, cb = g.force_sigmoid ? 0.f : -0.001f * om;
+                float c[32];
+                tmem_ld32(tmem + d2_col(n, pass, k) + lane_base_g, c);
+#pragma unroll
+                for (int x = 0; x < kRgb; ++x) c[x] = fmaf(rcp_approx(1.f + ex2_approx(c[x] + sm.b2c[x])), ca, cb);
+#pragma unroll
+                for (int t2 = 0; t2 < 32 / RPT; ++t2) {
+                    const int target = rl_first + t2;
+                    float r[32];
+#pragma unroll
+                    for (int x = 0; x < 32; ++x) r[x] = (RPT == 32 || rl == target) ? c[x] : 0.f;
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        const bool up = (lane & off) != 0;
+#pragma unroll
+                        for (int j = 0; j < off; ++j) {
+                            const float send = up ? r[j] : r[j + off];
+                            const float keep = up ? r[j + off] : r[j];
+                            r[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                        }
+                    }
+                    part[t2] += r[0];
+                }
+            }
+#pragma unroll
+            for (int t2 = 0; t2 < 32 / RPT; ++t2) sm.part[team][rl_first + t2][lane] = part[t2];
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.fa_free);
+#pragma unroll
+            for (int k = 0; k < 6; ++k)                                    // the load registers were free for the share: back to finite values
+#pragma unroll
+                for (int x = 0; x < 8; ++x) v[k][x] = 0.f;
+        };
         int it = 0;
         for (int q = 0; q < T; ++q) {
             const TileDesc td = tile_at(q, n_my);
@@ -202,6 +264,9 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             const long long ray0 = (long long)grp * GR;
             GroupState& st = sm.st[td.n & 3];
             tk_.lap(0);
+            // every team gathers exactly one tile of each pass: before its tile of F(n) it does its share of colours(n-1) - layer 2 of
+            // F(n) (which overwrites the shared fine area) waits for all twelve shares (fa_free)
+            if (kGCol && td.pass == 1 && td.n >= 1) { colour_share(td.n - 1); tk_.lap(15); }
             if (td.pass == 0) mbar_wait(&sm.state_free[td.n & 3], ((td.n >> 2) & 1) ^ 1);
             else mbar_wait(&sm.fine_ready[td.n & 3], (td.n >> 2) & 1);
             tk_.lap(1);                                                   // [1] wait state_free / fine_ready
@@ -308,6 +373,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             if (lane == 0) mbar_arrive(&sm.a1_full[stage]);
             tk_.lap(3);                                                   // [3] gather of one tile (32 rows)
         }
+        if (kGCol) colour_share(n_my - 1);
     } else if (warp < kGW + kEW) {
         // =========================================================================== EPILOGUE
         const int e = warp - kGW, quarter = e & 3, chunk = e >> 2;
@@ -404,7 +470,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             const TileDesc td = tile_at(q, n_my);
             // ---- epilogue 1: D1 -> softplus2 -> A2[buf]
             tk_.lap(4);
-            if (td.pass == 1 && td.k == 0 && td.n >= 1) { colours(td.n - 1); tk_.lap(11); }   // [11] colours (incl. wait for omega)
+            if (!kGCol && td.pass == 1 && td.k == 0 && td.n >= 1) { colours(td.n - 1); tk_.lap(11); }   // [11] colours (incl. wait for omega)
             mbar_wait(&sm.d1_full, it & 1);
             tk_.lap(5);                                                   // [5] wait d1_full
             tc_fence_after();
@@ -464,7 +530,7 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             if (td.k == 2) { sigma_read(it - 1, prev); tk_.lap(12); after_sigma_t(prev); have_prev = false; }
         }
         if (have_prev) { sigma_read(it - 1, prev); after_sigma_t(prev); }
-        colours(n_my - 1);
+        if (!kGCol) colours(n_my - 1);
     } else if (warp < kGW + kEW + kRW) {
         // =========================================================================== RAY (one warp per ray)
         const int rw = warp - kGW - kEW;
@@ -674,6 +740,19 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
             if (lane == 0) sl.back[rl] = back;
             __syncwarp();
         };
+        // GCOL: add the three per-team partial sums of group n in a fixed order, write the colours, release the group's state
+        auto finalize = [&](int n) {
+            mbar_wait(&sm.fa_free, n & 1);                                    // all twelve gather warps have published their share
+            SlotState& sl = sm.slot[n & 1];
+            const long long ray0 = (long long)((int)blockIdx.x + n * (int)gridDim.x) * GR;
+            for (int rl = rw; rl < GR; rl += kRW) {
+                const long long ray = ray0 + rl;
+                const float sum = __fadd_rn(__fadd_rn(sm.part[0][rl][lane], sm.part[1][rl][lane]), sm.part[2][rl][lane]);
+                if (ray < a.R) a.out_rgb[ray * kRgb + lane] = __fsub_rn(__fmul_rn(__fadd_rn(sum, sl.back[rl]), 2.f), 1.f);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.state_free[n & 3]);
+        };
         // tasks follow the pass schedule: importance(n) after C(n), merge(n) after F(n)
         Tick tr_(a.timing, blockIdx.x == 0 && rw == 0 && lane == 0);
         for (int j = 0; j < 2 * n_my; ++j) {
@@ -688,13 +767,15 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
                 tr_.lap(9);                                                   // [9] importance
             } else {
                 mbar_wait(&sm.sigf_ready[si], par);
-                if (n >= 2) mbar_wait(&sm.state_free[(n - 2) & 3], ((n - 2) >> 2) & 1);       // colours(n-2) has released the omega slot
-                tr_.lap(14);                                                  // [14] wait for fine sigma / slot
+                if (kGCol) { if (n >= 1) finalize(n - 1); }                   // shares of n-1 were taken at the start of this fine pass
+                else if (n >= 2) mbar_wait(&sm.state_free[(n - 2) & 3], ((n - 2) >> 2) & 1);   // colours(n-2) has released the omega slot
+                tr_.lap(14);                                                  // [14] wait for fine sigma / slot (GCOL: + finalize)
                 for (int rl = rw; rl < GR; rl += kRW) composite_ray(n, rl);
                 if (lane == 0) mbar_arrive(&sm.omega_ready[n & 1]);
                 tr_.lap(10);                                                  // [10] merge / weights
             }
         }
+        if (kGCol) finalize(n_my - 1);
     } else {
         // =========================================================================== MMA issuer (one thread)
         if (lane == 0) {
@@ -705,6 +786,9 @@ __global__ void __launch_bounds__(kThreadsWS, 1) k_render_ws3(const WsArgs a) {
                 const int buf = it2 & 1;
                 mbar_wait(&sm.a2_full[buf], (it2 >> 1) & 1);
                 mbar_wait(&sm.dsig_empty, (it2 & 1) ^ 1);
+                // GCOL: the shared fine area (and, later in the schedule, coarse area n % 3) is rewritten from here on - the
+                // gather warps must have taken the colours of the previous fine pass out of TMEM
+                if (kGCol && tp.pass == 1 && tp.k == 0 && tp.n >= 1) mbar_wait(&sm.fa_free, (tp.n - 1) & 1);
                 tc_fence_after();
                 const uint32_t a2h = smem_u32(sm.a2[buf][0]), a2l = smem_u32(sm.a2[buf][1]);
                 const uint32_t dc = tmem + d2_col(tp.n, tp.pass, tp.k), ds = tmem + kColSig;
@@ -814,9 +898,13 @@ int render_forward_fused_ws3(const Geom& g, const p3d_render_params* p, const vo
     }
     const size_t smem = sizeof(WsSmem) + 1024;
     void (*kern)(WsArgs) = nullptr;
-    const bool sc32 = g.stride_col == kC;
-    if (g.S == 96) kern = p->planes_bf16 ? (sc32 ? k_render_ws3<true, 96, kC> : k_render_ws3<true, 96, 0>) : (sc32 ? k_render_ws3<false, 96, kC> : k_render_ws3<false, 96, 0>);
-    else kern = p->planes_bf16 ? (sc32 ? k_render_ws3<true, 48, kC> : k_render_ws3<true, 48, 0>) : (sc32 ? k_render_ws3<false, 48, kC> : k_render_ws3<false, 48, 0>);
+    // the x+1 texel is an immediate offset when the texel stride is one of the two layouts the host produces: kC (the layout
+    // pre-pass: one plane's texels contiguous) or 3 kC (a (N,96,H,W) channels_last backbone output consumed zero-copy)
+    const int sc = g.stride_col == kC ? 1 : (g.stride_col == 3 * kC ? 2 : 0);
+#define P3D_PICK(BF, S_) (sc == 1 ? k_render_ws3<BF, S_, kC> : (sc == 2 ? k_render_ws3<BF, S_, 3 * kC> : k_render_ws3<BF, S_, 0>))
+    if (g.S == 96) kern = p->planes_bf16 ? P3D_PICK(true, 96) : P3D_PICK(false, 96);
+    else kern = p->planes_bf16 ? P3D_PICK(true, 48) : P3D_PICK(false, 48);
+#undef P3D_PICK
     P3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = a.n_groups < n_sm ? a.n_groups : n_sm;
     {
@@ -829,10 +917,10 @@ int render_forward_fused_ws3(const Geom& g, const p3d_render_params* p, const vo
         P3D_CUDA_TRY(cudaMemcpyAsync(h, d_timing, sizeof(h), cudaMemcpyDeviceToHost, stream));
         P3D_CUDA_TRY(cudaStreamSynchronize(stream));
         const int groups_cta0 = (a.n_groups + grid - 1) / grid;
-        fprintf(stderr, "[p3d ws timing, CTA0, cycles/group over %d groups] G(warp0: 1/3 of tiles): wait_dep %.0f wait_ring %.0f gather %.0f | "
+        fprintf(stderr, "[p3d ws timing, CTA0, cycles/group over %d groups] G(warp0: 1/3 of tiles): wait_dep %.0f wait_ring %.0f gather %.0f share %.0f | "
                         "E(warp0): wait_d1 %.0f ld_d1 %.0f wait_a2 %.0f epi1 %.0f sigma %.0f colours(+omega wait) %.0f other %.0f | "
                         "R(warp0): wait_sigc %.0f importance %.0f wait_sigf %.0f merge %.0f\n",
-                groups_cta0, (double)h[1] / groups_cta0, (double)h[2] / groups_cta0, (double)h[3] / groups_cta0, (double)h[5] / groups_cta0,
+                groups_cta0, (double)h[1] / groups_cta0, (double)h[2] / groups_cta0, (double)h[3] / groups_cta0, (double)h[15] / groups_cta0, (double)h[5] / groups_cta0,
                 (double)h[6] / groups_cta0, (double)h[7] / groups_cta0, (double)h[8] / groups_cta0, (double)h[12] / groups_cta0,
                 (double)h[11] / groups_cta0, (double)(h[0] + h[4]) / groups_cta0, (double)h[13] / groups_cta0, (double)h[9] / groups_cta0,
                 (double)h[14] / groups_cta0, (double)h[10] / groups_cta0);

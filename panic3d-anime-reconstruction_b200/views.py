@@ -52,38 +52,61 @@ def gather_views(local: torch.Tensor, n_views: int, dst: Optional[int] = None, g
     return torch.cat([o[:c] for o, c in zip(out, counts)]) if rank == dst else None
 
 
+class _RawCuda:
+    """__cuda_array_interface__ view of raw device memory (zero-copy torch.as_tensor)."""
+
+    def __init__(self, ptr, shape, typestr='<f4'):
+        self.__cuda_array_interface__ = {'shape': tuple(shape), 'typestr': typestr, 'data': (int(ptr), False), 'version': 2}
+
+
 class PeerGather:
     """Rendered images -> the consumer rank, overlapped with the next render.
 
-    The NCCL gather is an SM kernel; the fused renderer is a persistent kernel that owns every SM (1 CTA/SM, 227 KB of
+    The NCCL gather is an SM kernel; the fused renderer is a persistent kernel that owns every SM (1 CTA/SM, 224 KB of
     shared memory), so a collective launched beside it cannot start before the render ends - the exchange sits on the
-    critical path of every step.  Here the consumer rank exports ONE device buffer (`slots` x world x shard) through CUDA
-    IPC; every other rank maps it once and from then on delivers its shard with a peer-to-peer `copy_` on a side stream:
-    an NVLink DMA by the copy engines, no SM, no NCCL kernel, so it runs under the next step's render.  `fence()` makes
-    the consumer's view complete (side streams drained + one barrier); a consumer that streams results polls per slot.
-    Falls back to `gather_views` when the backend is not NCCL / the tensors are not CUDA (the CPU tests)."""
+    critical path of every step.  Here the consumer rank allocates ONE device buffer (`slots` x world x shard) in the
+    library and exports it (`p3d_ipc_alloc`: cudaIpcGetMemHandle); every other rank opens the handle on ITS OWN device
+    (`p3d_ipc_open`: the driver enables peer access over NVLink lazily) and from then on delivers its shard with
+    `p3d_copy_async` on a side stream: an NVLink DMA by the copy engines, no SM, no NCCL kernel, so it runs under the next
+    step's render.  `fence()` makes the consumer's view complete (side streams drained + one barrier); NCCL stays the
+    plumbing (handle broadcast, barrier).  Falls back to `gather_views` when the backend is not NCCL / the tensors are not
+    CUDA (the CPU tests).  fp32 shards only."""
 
     def __init__(self, shard_shape, dtype, device, dst: int = 0, group=None, slots: int = 2):
         self.group, self.dst, self.slots = group, dst, slots
+        self.shard_shape = tuple(shard_shape)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.p2p = self.world > 1 and torch.device(device).type == 'cuda' and dist.get_backend(group) == 'nccl'
-        self.buf = self.remote = None
+        self.p2p = (self.world > 1 and torch.device(device).type == 'cuda' and dist.get_backend(group) == 'nccl'
+                    and dtype == torch.float32)
+        self.buf = None
         self.last = None
+        self._base = None
         if not self.p2p:
             return
-        from torch.multiprocessing.reductions import reduce_tensor
+        import ctypes as C
+        from . import _lib
+        self._lib, self._C = _lib, C
+        L = _lib.lib()
+        n = 1
+        for d in self.shard_shape:
+            n *= int(d)
+        self.shard_bytes = n * 4
+        total = slots * self.world * self.shard_bytes
         box = [None]
-        if self.rank == dst:
-            self.buf = torch.zeros((slots, self.world) + tuple(shard_shape), dtype=dtype, device=device)
-            box[0] = reduce_tensor(self.buf)                       # (rebuild_fn, args) carrying the cudaIpcMemHandle
-        dist.broadcast_object_list(box, src=dst, group=group)
-        if self.rank == dst:
-            self.remote = self.buf
-        else:
-            fn, fargs = box[0]
-            self.remote = fn(*fargs)                                # dst's memory mapped into this process (peer access over NVLink)
-        self.stream = torch.cuda.Stream(device=device)
+        ptr = C.c_void_p()
+        with torch.cuda.device(device):
+            if self.rank == dst:
+                handle = C.create_string_buffer(64)
+                _lib.check(L.p3d_ipc_alloc(total, C.byref(ptr), handle))
+                box[0] = handle.raw
+            dist.broadcast_object_list(box, src=dst, group=group)
+            if self.rank != dst:
+                _lib.check(L.p3d_ipc_open(box[0], C.byref(ptr)))
+            self._base = int(ptr.value)
+            if self.rank == dst:
+                self.buf = torch.as_tensor(_RawCuda(self._base, (slots, self.world) + self.shard_shape), device=device)
+            self.stream = torch.cuda.Stream(device=device)
         dist.barrier(group=group)
 
     def push(self, shard: torch.Tensor, step: int = 0):
@@ -91,10 +114,11 @@ class PeerGather:
         if not self.p2p:
             self.last = gather_views(shard, shard.shape[0] * self.world, self.dst, self.group)
             return
+        assert shard.is_contiguous() and shard.dtype == torch.float32 and shard.numel() * 4 == self.shard_bytes
         cur = torch.cuda.current_stream(shard.device)
         self.stream.wait_stream(cur)
-        with torch.cuda.stream(self.stream):
-            self.remote[step % self.slots, self.rank].copy_(shard, non_blocking=True)
+        dst = self._base + ((step % self.slots) * self.world + self.rank) * self.shard_bytes
+        self._lib.check(self._lib.lib().p3d_copy_async(dst, shard.data_ptr(), self.shard_bytes, self.stream.cuda_stream))
         shard.record_stream(self.stream)
 
     def join_current_stream(self):
@@ -115,6 +139,13 @@ class PeerGather:
             return None
         b = self.buf[step % self.slots]
         return b.reshape((b.shape[0] * b.shape[1],) + tuple(b.shape[2:]))
+
+    def close(self):
+        if self.p2p and self._base:
+            self.fence()
+            L = self._lib.lib()
+            (L.p3d_ipc_free if self.rank == self.dst else L.p3d_ipc_close)(self._base)
+            self._base, self.buf = None, None
 
 
 def render_sharded(renderer, planes, decoder, ray_origins, ray_directions, options, dst: Optional[int] = 0, exact_depth: bool = True,

@@ -61,7 +61,9 @@ class Sim:
         self.a1_full = [B(4) for _ in range(K_NA)]; self.a1_empty = [B(1) for _ in range(K_NA)]
         self.a2_full = [B(K_EW) for _ in range(2)]; self.a2_empty = [B(1) for _ in range(2)]
         self.d1_full, self.d1_empty, self.d2_full, self.dsig_empty = B(1), B(K_EW), B(1), B(4)
-        self.fine_ready = [B(K_RW) for _ in range(4)]; self.state_free = [B(1) for _ in range(4)]
+        self.fine_ready = [B(K_RW) for _ in range(4)]; self.state_free = [B(K_RW) for _ in range(4)]      # released by the ray warps' finalize
+        self.fa_free = B(12)                          # the twelve gather warps' colour shares of a group have left TMEM
+        self.share_count = {}
         self.sigc_ready = [B(4) for _ in range(4)]; self.sigf_ready = [B(4) for _ in range(4)]
         self.omega_ready = [B(K_RW) for _ in range(2)]
         self.now, self.events, self.seq = 0.0, [], 0
@@ -72,6 +74,7 @@ class Sim:
         self.state_owner = [None] * 4
         self.slot_owner = [None] * 2
         self.d1_unread, self.sig_unread = False, False
+        self.part_owner, self.finalized = None, set()
         self.ebar_count, self.ebar_gen = 0, 0
 
     def dur(self, lo, hi):
@@ -84,15 +87,29 @@ class Sim:
     # ---------------------------------------------------------------- roles (generators yield ('wait', bar, parity) | ('work', dt) | ('ebar',))
     def gather_warp(self, gw):
         team, it = gw >> 2, 0
+
+        def colour_share(n):                          # this warp's share of colours(n): tiles 2*team, 2*team+1 of its TMEM lane quarter
+            yield ('wait', self.omega_ready[n & 1], (n >> 1) & 1)
+            assert n in self.composite_done and self.slot_owner[n & 1] == n
+            assert self.tiles_written.get(n, set()) == {(p, k) for p in (0, 1) for k in range(3)}, f'colour share of {n} before all six tiles'
+            assert self.part_owner is None or self.part_owner == n or self.part_owner in self.finalized, 'partial sums overwritten before finalize'
+            self.part_owner = n
+            yield ('work', self.dur(0.5, 3))
+            self.share_count[n] = self.share_count.get(n, 0) + 1
+            if self.share_count[n] == 12:
+                self.colours_done.add(n)
+            self.fa_free.arrive()
         for q in range(self.T):
             n, p, k = tile_at(q, self.N)
             my_it = it; it += 1
             if my_it % K_TEAMS != team:
                 continue
+            if p == 1 and n >= 1:
+                yield from colour_share(n - 1)
             if p == 0:
                 yield ('wait', self.state_free[n & 3], ((n >> 2) & 1) ^ 1)
                 prev = self.state_owner[n & 3]
-                assert prev is None or prev == n or prev in self.colours_done, f'state slot of group {prev} rewritten for {n}'
+                assert prev is None or prev == n or prev in self.finalized, f'state slot of group {prev} rewritten for {n}'
                 self.state_owner[n & 3] = n
             else:
                 yield ('wait', self.fine_ready[n & 3], (n >> 2) & 1)
@@ -101,6 +118,7 @@ class Sim:
             yield ('wait', self.a1_empty[stage], ((my_it // K_NA) & 1) ^ 1)
             yield ('work', self.dur(5, 20))
             self.a1_full[stage].arrive()
+        yield from colour_share(self.N - 1)
 
     def mma_thread(self):
         it, prev = 0, None
@@ -110,6 +128,8 @@ class Sim:
             buf = it2 & 1
             yield ('wait', self.a2_full[buf], (it2 >> 1) & 1)
             yield ('wait', self.dsig_empty, (it2 & 1) ^ 1)
+            if p == 1 and k == 0 and n >= 1:
+                yield ('wait', self.fa_free, (n - 1) & 1)
             area = ('CA', n % 3, k) if p == 0 else ('FA', k)
             owner = self.area_owner.get(area)
             assert owner is None or owner in self.colours_done, f'layer 2 of {tp} overwrites {area} of group {owner} before its colours'
@@ -171,8 +191,6 @@ class Sim:
                 self.state_free[n & 3].arrive()
         for q in range(self.T):
             td = tile_at(q, self.N)
-            if td[1] == 1 and td[2] == 0 and td[0] >= 1:
-                yield from colours(td[0] - 1)
             yield ('wait', self.d1_full, it & 1)
             yield ('work', self.dur(0.2, 1))
             reads['d1'] += 1
@@ -192,9 +210,17 @@ class Sim:
                 prev = None
         if prev is not None:
             yield from sigma_read(it - 1, prev)
-        yield from colours(self.N - 1)
 
     def ray_warp(self, rw):
+        def finalize(n):                              # fixed-order sum of the three per-team partials, out_rgb, release the group's state
+            yield ('wait', self.fa_free, n & 1)
+            assert n in self.colours_done and self.part_owner == n
+            yield ('work', self.dur(0.05, 0.3))
+            self.fin_count = getattr(self, 'fin_count', {})
+            self.fin_count[n] = self.fin_count.get(n, 0) + 1
+            if self.fin_count[n] == K_RW:
+                self.finalized.add(n)
+            self.state_free[n & 3].arrive()
         for j in range(2 * self.N):
             n, p = pass_at(j, self.N)
             si, par = n & 3, (n >> 2) & 1
@@ -206,8 +232,9 @@ class Sim:
                 self.fine_ready[si].arrive()
             else:
                 yield ('wait', self.sigf_ready[si], par)
+                if n >= 1:
+                    yield from finalize(n - 1)
                 if n >= 2:
-                    yield ('wait', self.state_free[(n - 2) & 3], ((n - 2) >> 2) & 1)
                     assert (n - 2) in self.colours_done
                 prev = self.slot_owner[n & 1]
                 assert prev is None or prev == n or prev in self.colours_done, f'omega slot of group {prev} rewritten for {n}'
@@ -216,6 +243,7 @@ class Sim:
                 if rw == 0:
                     self.composite_done.add(n)
                 self.omega_ready[n & 1].arrive()
+        yield from finalize(self.N - 1)
 
     def procs(self):
         return ([('G%d' % g, self.gather_warp(g)) for g in range(12)] + [('M', self.mma_thread())] +
@@ -284,6 +312,8 @@ class SimV3(Sim):
         super().__init__(N, seed)
         self.T = 12 * ((N + 1) // 2)
         self.fine_ready = [Bar(1) for _ in range(4)]
+        self.state_free = [Bar(1) for _ in range(4)]        # released by epilogue warp 0 after colours(n)
+        self.finalized = self.colours_done                   # that kernel has no separate finalize step
 
     def tiles(self):
         return [t for t in (tile_at_v3(q) for q in range(self.T)) if t[0] < self.N]
@@ -299,7 +329,7 @@ class SimV3(Sim):
             if p == 0:
                 yield ('wait', self.state_free[n & 3], ((n >> 2) & 1) ^ 1)
                 prev = self.state_owner[n & 3]
-                assert prev is None or prev == n or prev in self.colours_done, f'state slot of group {prev} rewritten for {n}'
+                assert prev is None or prev == n or prev in self.finalized, f'state slot of group {prev} rewritten for {n}'
                 self.state_owner[n & 3] = n
             else:
                 yield ('wait', self.fine_ready[n & 3], (n >> 2) & 1)
