@@ -55,17 +55,25 @@ class Bar:
 
 
 class Sim:
-    def __init__(self, N, seed):
+    def __init__(self, N, seed, gcol=False, altsig=False):
+        # gcol / altsig: two protocol experiments that were built, parity-tested and measured slower than the shipped kernel
+        # (profiles/experiments/render_fused_ws3_switches.cu.txt, profiles/r2_kernel_log.md); both False = csrc/render_fused_ws3.cu.
+        # gcol: colour reduction shared by the gather warps, finalised by the ray warps
+        self.gcol = gcol
+        # altsig: the two column halves of the epilogue role read sigma back in turns (tile parity), d2_full is
+        # one barrier per tile parity so that each half observes every phase of its own, sigc/sigf_ready take one arrival per warp-tile
+        self.altsig = altsig
         self.N, self.T, self.rng = N, 6 * N, random.Random(seed)
         B = Bar
         self.a1_full = [B(4) for _ in range(K_NA)]; self.a1_empty = [B(1) for _ in range(K_NA)]
         self.a2_full = [B(K_EW) for _ in range(2)]; self.a2_empty = [B(1) for _ in range(2)]
-        self.d1_full, self.d1_empty, self.d2_full, self.dsig_empty = B(1), B(K_EW), B(1), B(4)
-        self.fine_ready = [B(K_RW) for _ in range(4)]; self.state_free = [B(K_RW) for _ in range(4)]      # released by the ray warps' finalize
+        self.d1_full, self.d1_empty, self.d2_full, self.dsig_empty = B(1), B(K_EW), ([B(1), B(1)] if altsig else B(1)), B(4)
+        self.fine_ready = [B(K_RW) for _ in range(4)]; self.state_free = [B(K_RW if gcol else 1) for _ in range(4)]   # gcol: released by the ray warps' finalize
         self.fa_free = B(12)                          # the twelve gather warps' colour shares of a group have left TMEM
         self.share_count = {}
-        self.sigc_ready = [B(4) for _ in range(4)]; self.sigf_ready = [B(4) for _ in range(4)]
+        self.sigc_ready = [B(12 if altsig else 4) for _ in range(4)]; self.sigf_ready = [B(12 if altsig else 4) for _ in range(4)]
         self.omega_ready = [B(K_RW) for _ in range(2)]
+        self.sig_tile = None
         self.now, self.events, self.seq = 0.0, [], 0
         # hazard bookkeeping
         self.area_owner = {}                          # TMEM colour area -> (group, tiles written)
@@ -74,7 +82,7 @@ class Sim:
         self.state_owner = [None] * 4
         self.slot_owner = [None] * 2
         self.d1_unread, self.sig_unread = False, False
-        self.part_owner, self.finalized = None, set()
+        self.part_owner, self.finalized = None, (set() if gcol else self.colours_done)
         self.ebar_count, self.ebar_gen = 0, 0
 
     def dur(self, lo, hi):
@@ -104,7 +112,7 @@ class Sim:
             my_it = it; it += 1
             if my_it % K_TEAMS != team:
                 continue
-            if p == 1 and n >= 1:
+            if self.gcol and p == 1 and n >= 1:
                 yield from colour_share(n - 1)
             if p == 0:
                 yield ('wait', self.state_free[n & 3], ((n >> 2) & 1) ^ 1)
@@ -118,7 +126,8 @@ class Sim:
             yield ('wait', self.a1_empty[stage], ((my_it // K_NA) & 1) ^ 1)
             yield ('work', self.dur(5, 20))
             self.a1_full[stage].arrive()
-        yield from colour_share(self.N - 1)
+        if self.gcol:
+            yield from colour_share(self.N - 1)
 
     def mma_thread(self):
         it, prev = 0, None
@@ -128,7 +137,7 @@ class Sim:
             buf = it2 & 1
             yield ('wait', self.a2_full[buf], (it2 >> 1) & 1)
             yield ('wait', self.dsig_empty, (it2 & 1) ^ 1)
-            if p == 1 and k == 0 and n >= 1:
+            if self.gcol and p == 1 and k == 0 and n >= 1:
                 yield ('wait', self.fa_free, (n - 1) & 1)
             area = ('CA', n % 3, k) if p == 0 else ('FA', k)
             owner = self.area_owner.get(area)
@@ -139,7 +148,8 @@ class Sim:
             def done():
                 self.tiles_written.setdefault(n, set()).add((p, k))
                 self.sig_unread = True
-                self.d2_full.arrive(); self.a2_empty[buf].arrive()
+                self.sig_tile = tp
+                (self.d2_full[it2 & 1] if self.altsig else self.d2_full).arrive(); self.a2_empty[buf].arrive()
             self.later(self.dur(0.2, 2), done)
         for q in range(self.T):
             td = tile_at(q, self.N)
@@ -166,16 +176,22 @@ class Sim:
         reads = {'d1': 0}
 
         def sigma_read(it_prev, tp):
-            if chunk != 0:
-                return
             n, p, k = tp
-            yield ('wait', self.d2_full, it_prev & 1)
+            if self.altsig:
+                if chunk != (it_prev & 1):
+                    return
+                yield ('wait', self.d2_full[it_prev & 1], (it_prev >> 1) & 1)
+            else:
+                if chunk != 0:
+                    return
+                yield ('wait', self.d2_full, it_prev & 1)
+            assert self.sig_tile == tp, f'sigma read-back of {tp} found the accumulator of {self.sig_tile}'
             yield ('work', self.dur(0.2, 1))
             self.sig_unread_readers = getattr(self, 'sig_unread_readers', 0) + 1
             if self.sig_unread_readers == 4:
                 self.sig_unread_readers, self.sig_unread = 0, False
             self.dsig_empty.arrive()
-            if k == 2:
+            if self.altsig or k == 2:
                 (self.sigc_ready if p == 0 else self.sigf_ready)[n & 3].arrive()
 
         def colours(n):
@@ -191,6 +207,8 @@ class Sim:
                 self.state_free[n & 3].arrive()
         for q in range(self.T):
             td = tile_at(q, self.N)
+            if not self.gcol and td[1] == 1 and td[2] == 0 and td[0] >= 1:
+                yield from colours(td[0] - 1)
             yield ('wait', self.d1_full, it & 1)
             yield ('work', self.dur(0.2, 1))
             reads['d1'] += 1
@@ -210,6 +228,8 @@ class Sim:
                 prev = None
         if prev is not None:
             yield from sigma_read(it - 1, prev)
+        if not self.gcol:
+            yield from colours(self.N - 1)
 
     def ray_warp(self, rw):
         def finalize(n):                              # fixed-order sum of the three per-team partials, out_rgb, release the group's state
@@ -232,9 +252,11 @@ class Sim:
                 self.fine_ready[si].arrive()
             else:
                 yield ('wait', self.sigf_ready[si], par)
-                if n >= 1:
+                if self.gcol and n >= 1:
                     yield from finalize(n - 1)
                 if n >= 2:
+                    if not self.gcol:
+                        yield ('wait', self.state_free[(n - 2) & 3], ((n - 2) >> 2) & 1)
                     assert (n - 2) in self.colours_done
                 prev = self.slot_owner[n & 1]
                 assert prev is None or prev == n or prev in self.colours_done, f'omega slot of group {prev} rewritten for {n}'
@@ -243,7 +265,8 @@ class Sim:
                 if rw == 0:
                     self.composite_done.add(n)
                 self.omega_ready[n & 1].arrive()
-        yield from finalize(self.N - 1)
+        if self.gcol:
+            yield from finalize(self.N - 1)
 
     def procs(self):
         return ([('G%d' % g, self.gather_warp(g)) for g in range(12)] + [('M', self.mma_thread())] +
@@ -313,6 +336,8 @@ class SimV3(Sim):
         self.T = 12 * ((N + 1) // 2)
         self.fine_ready = [Bar(1) for _ in range(4)]
         self.state_free = [Bar(1) for _ in range(4)]        # released by epilogue warp 0 after colours(n)
+        self.altsig, self.d2_full = False, Bar(1)
+        self.sigc_ready = [Bar(4) for _ in range(4)]; self.sigf_ready = [Bar(4) for _ in range(4)]
         self.finalized = self.colours_done                   # that kernel has no separate finalize step
 
     def tiles(self):
@@ -460,6 +485,23 @@ def test_pass_schedule_visits_every_group_once_in_a_valid_order():
 def test_protocol_has_no_deadlock_or_hazard(N):
     for seed in range(12):
         Sim(N, seed * 101 + N).run()
+
+
+@pytest.mark.parametrize('N', [1, 2, 3, 5, 8])
+def test_alternating_sigma_read_back_variant_has_no_deadlock_or_hazard(N):
+    """P3D_W3_ALTSIG=1 of the experiments file: the sigma read-back alternates between the column halves of the epilogue role;
+    d2_full is one barrier per tile parity (a single barrier would alias phases for a half that skips every other one - the
+    sig_tile assertion in sigma_read is what catches that)."""
+    for seed in range(6):
+        Sim(N, seed * 17 + N, altsig=True).run()
+
+
+@pytest.mark.parametrize('N', [1, 2, 3, 4, 5, 8, 11])
+def test_gather_side_colour_share_variant_has_no_deadlock_or_hazard(N):
+    """P3D_W3_GCOL=1 of the experiments file (colour reduction on the gather warps, finalize on the ray warps, fa_free hand-off to
+    the MMA thread)."""
+    for seed in range(8):
+        Sim(N, seed * 131 + N, gcol=True).run()
 
 
 @pytest.mark.parametrize('N', [1, 2, 3, 4, 5, 6, 7, 9, 12])
