@@ -486,7 +486,7 @@ def run_ours(args):
                'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(world, args.mlp, args.planes), 'clocks': clocks,
                'gpu_launches': int(launches), 'roofline': roof}
         if world > 1:
-            out['comm'] = {'mode': gather_mode, 'bytes_per_rank_per_step': VIEWS * R * R * 32 * 4, 'ms_per_step': comm_ms,
+            out['comm'] = {'mode': gather_mode if (peer is None or peer.p2p) else 'nccl (p2p unavailable on this box)', 'bytes_per_rank_per_step': VIEWS * R * R * 32 * 4, 'ms_per_step': comm_ms,
                            'note': 'rendered feature images -> rank 0; p2p = NVLink DMA on a side stream under the next render'}
         if e2e is not None:
             out['e2e'] = {'value': world * VIEWS * e2e['steps'] / (e2e['ms'] * 1e-3), 'unit': UNIT,

@@ -68,7 +68,7 @@ def main():
     peak, src = hbm_peak()
     flush = torch.zeros(192 * 1024 * 1024 // 4, device=dev)          # 192 MB > 126 MB L2
     f4 = upfirdn2d.setup_filter([1, 3, 3, 1], device=dev)
-    f12 = upfirdn2d.setup_filter(torch.hann_window(14)[1:-1].numpy())   # 12 taps, separable
+    f12 = upfirdn2d.setup_filter(torch.hann_window(14)[1:-1].numpy(), device=dev)   # 12 taps, separable
     out = []
 
     def rec(op, case, dtype, x_elems, y_elems, fn):

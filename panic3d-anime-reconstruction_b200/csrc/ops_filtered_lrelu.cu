@@ -53,17 +53,30 @@ __device__ __forceinline__ float tap(const float* f, int fh, int fw, int sep, in
     return sep ? f[yy] * f[xx] : f[yy * fw + xx];
 }
 
-template <typename T>
+// SEP: both filters were given as 1-D taps (the way StyleGAN3 layers and setup_filter(>= 8 taps) pass them).  The two FIRs then run as
+// four 1-D passes through shared memory - up-x, up-y (+ activation / signs), down-x, down-y - e.g. 6+6 and 12+12 instead of 36 and 144
+// multiply-adds per up-sampled / output pixel for the 12-tap up 2 / down 2 layer; the rounding differs from the 2-D sum in the last bit.
+template <typename T, bool SEP>
 __global__ void __launch_bounds__(kThr) k_filtered_lrelu(const FlParams p) {
     extern __shared__ float smem[];
-    float* s_wu = smem;                                   // fuH*fuW (gain up^2*gain folded)
-    float* s_wd = s_wu + p.fuH * p.fuW;                   // fdH*fdW
-    float* s_in = s_wd + p.fdH * p.fdW;                   // inTH*inTW
+    float* s_wu = smem;                                   // fuH*fuW (gain up^2*gain folded)   SEP: 2 x fuW (x taps with the gain, y taps)
+    float* s_wd = s_wu + (SEP ? 2 * p.fuW : p.fuH * p.fuW);   // fdH*fdW                        SEP: fdW
+    float* s_in = s_wd + (SEP ? p.fdW : p.fdH * p.fdW);   // inTH*inTW
     float* s_up = s_in + p.inTH * p.inTW;                 // upTH*upTW
+    float* s_t1 = s_up + p.upTH * p.upTW;                 // SEP: inTH*upTW  rows of the input footprint after the horizontal up-pass
+    float* s_t2 = s_t1 + p.inTH * p.upTW;                 // SEP: upTH*kOutW rows of the activated tile after the horizontal down-pass
     const int tid = threadIdx.x;
     const float ugain = (float)p.up * (float)p.up * p.gain;
-    for (int i = tid; i < p.fuH * p.fuW; i += kThr) s_wu[i] = tap(p.fu, p.fuH, p.fuW, p.fuSep, i / p.fuW, i % p.fuW, p.flip) * ugain;
-    for (int i = tid; i < p.fdH * p.fdW; i += kThr) s_wd[i] = tap(p.fd, p.fdH, p.fdW, p.fdSep, i / p.fdW, i % p.fdW, p.flip);
+    if (SEP) {
+        for (int i = tid; i < p.fuW; i += kThr) {
+            const float t = p.fu[p.flip ? i : p.fuW - 1 - i];
+            s_wu[i] = t * ugain; s_wu[p.fuW + i] = t;
+        }
+        for (int i = tid; i < p.fdW; i += kThr) s_wd[i] = p.fd[p.flip ? i : p.fdW - 1 - i];
+    } else {
+        for (int i = tid; i < p.fuH * p.fuW; i += kThr) s_wu[i] = tap(p.fu, p.fuH, p.fuW, p.fuSep, i / p.fuW, i % p.fuW, p.flip) * ugain;
+        for (int i = tid; i < p.fdH * p.fdW; i += kThr) s_wd[i] = tap(p.fd, p.fdH, p.fdW, p.fdSep, i / p.fdW, i % p.fdW, p.flip);
+    }
 
     const int tile = blockIdx.x, tyi = tile / p.tilesX, txi = tile - tyi * p.tilesX;
     const int ox0 = txi * kOutW, oy0 = tyi * kOutH;
@@ -89,6 +102,19 @@ __global__ void __launch_bounds__(kThr) k_filtered_lrelu(const FlParams p) {
             s_in[i] = (iy >= 0 && iy < p.inH && ix >= 0 && ix < p.inW) ? Fx<T>::ld(xi[iy * p.xs[2] + ix * p.xs[3]]) + bias : 0.f;
         }
         __syncthreads();
+        if (SEP) {
+            // ---- B1) horizontal up-pass over every footprint row
+            for (int i = tid; i < p.inTH * p.upTW; i += kThr) {
+                const int r = i / p.upTW, q = i - r * p.upTW;
+                const int tx0 = ux0 + q - p.px0;
+                const int kx0 = pmod(-tx0, p.up);
+                const float* row = s_in + r * p.inTW + ((tx0 + kx0) / p.up - ix0);
+                float acc = 0.f;
+                for (int kx = kx0, j = 0; kx < p.fuW; kx += p.up, ++j) acc = fmaf(row[j], s_wu[kx], acc);
+                s_t1[i] = acc;
+            }
+            __syncthreads();
+        }
         // ---- B) up-FIR + activation, 4-wide strips
         const int strips = (p.upTW + 3) >> 2;
         unsigned char* srow_base = p.s ? p.s + (size_t)img * p.sH * (p.sW >> 2) : nullptr;
@@ -105,6 +131,10 @@ __global__ void __launch_bounds__(kThr) k_filtered_lrelu(const FlParams p) {
                 const int ux = ux0 + q4 + e;
                 float acc = 0.f;
                 if (q4 + e < p.upTW && uy < p.upH && ux < p.upW) {
+                    if (SEP) {                             // vertical up-pass over the horizontally filtered rows
+                        const float* col = s_t1 + sy0 * p.upTW + q4 + e;
+                        for (int ky = ky0, j = 0; ky < p.fuW; ky += p.up, ++j) acc = fmaf(col[j * p.upTW], s_wu[p.fuW + ky], acc);
+                    } else {
                     const int tx0 = ux - p.px0;
                     const int kx0 = pmod(-tx0, p.up);
                     const int sx0 = (tx0 + kx0) / p.up - ix0;
@@ -112,6 +142,7 @@ __global__ void __launch_bounds__(kThr) k_filtered_lrelu(const FlParams p) {
                         const float* row = s_in + sy * p.inTW + sx0;
                         const float* wr = s_wu + ky * p.fuW;
                         for (int kx = kx0, j = 0; kx < p.fuW; kx += p.up, ++j) acc = fmaf(row[j], wr[kx], acc);
+                    }
                     }
                     if (p.sign_mode == 2) {                // gradient pass: gate by the stored signs
                         const int qx = ux + p.sx, qy = uy + p.sy;
@@ -138,6 +169,17 @@ __global__ void __launch_bounds__(kThr) k_filtered_lrelu(const FlParams p) {
             }
         }
         __syncthreads();
+        if (SEP) {
+            // ---- C1) horizontal down-pass over every row of the activated tile
+            for (int i = tid; i < p.upTH * kOutW; i += kThr) {
+                const int r = i / kOutW, tx = i - r * kOutW;
+                const float* base = s_up + r * p.upTW + tx * p.down;
+                float acc = 0.f;
+                for (int kx = 0; kx < p.fdW; ++kx) acc = fmaf(base[kx], s_wd[kx], acc);
+                s_t2[i] = acc;
+            }
+            __syncthreads();
+        }
         // ---- C) down-FIR
         for (int i = tid; i < kOutW * kOutH; i += kThr) {
             const int ty = i / kOutW, tx = i - ty * kOutW;
@@ -145,6 +187,10 @@ __global__ void __launch_bounds__(kThr) k_filtered_lrelu(const FlParams p) {
             if (ox >= p.outW || oy >= p.outH) continue;
             const float* base = s_up + (ty * p.down) * p.upTW + tx * p.down;
             float acc = 0.f;
+            if (SEP) {
+                const float* col = s_t2 + (ty * p.down) * kOutW + tx;
+                for (int ky = 0; ky < p.fdW; ++ky) acc = fmaf(col[ky * kOutW], s_wd[ky], acc);
+            } else
             for (int ky = 0; ky < p.fdH; ++ky)
                 for (int kx = 0; kx < p.fdW; ++kx) acc = fmaf(base[ky * p.upTW + kx], s_wd[ky * p.fdW + kx], acc);
             yp[n * p.ys[0] + c * p.ys[1] + oy * p.ys[2] + ox * p.ys[3]] = Fx<T>::st(acc);
@@ -160,15 +206,18 @@ int launch_fl(FlParams p, cudaStream_t stream) {
     p.upTH = kOutH * p.down + p.fdH - 1 - (p.down - 1);
     p.inTW = (p.upTW + p.fuW - 1 + p.up - 1) / p.up + 1;
     p.inTH = (p.upTH + p.fuH - 1 + p.up - 1) / p.up + 1;
-    const size_t smem = ((size_t)p.fuH * p.fuW + (size_t)p.fdH * p.fdW + (size_t)p.inTW * p.inTH + (size_t)p.upTW * p.upTH) * sizeof(float);
+    const bool sep = p.fuSep && p.fdSep;
+    const size_t smem = sep ? ((size_t)2 * p.fuW + p.fdW + (size_t)p.inTW * p.inTH + (size_t)p.upTW * p.upTH + (size_t)p.inTH * p.upTW + (size_t)p.upTH * kOutW) * sizeof(float)
+                            : ((size_t)p.fuH * p.fuW + (size_t)p.fdH * p.fdW + (size_t)p.inTW * p.inTH + (size_t)p.upTW * p.upTH) * sizeof(float);
     if (smem > 200 * 1024) {
         set_error("filtered_lrelu: tile needs %zu bytes of shared memory (filters %dx%d / %dx%d, up %d, down %d)", smem, p.fuH, p.fuW, p.fdH, p.fdW, p.up, p.down);
         return P3D_EUNSUPPORTED;
     }
-    if (smem > 48 * 1024) P3D_CUDA_TRY(cudaFuncSetAttribute(k_filtered_lrelu<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    auto kern = sep ? k_filtered_lrelu<T, true> : k_filtered_lrelu<T, false>;
+    if (smem > 48 * 1024) P3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const long long nc = (long long)p.N * p.C;
     dim3 grid((unsigned)(p.tilesX * p.tilesY), (unsigned)(nc < 32768 ? nc : 32768));
-    k_filtered_lrelu<T><<<grid, kThr, smem, stream>>>(p);
+    kern<<<grid, kThr, smem, stream>>>(p);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
 }

@@ -405,6 +405,67 @@ __global__ void __launch_bounds__(kThreads) k_upfirdn2d_strided(const UpfirdnPar
     }
 }
 
+// ------------------------------------------------------------------------------------------ channels-last (C fastest in x and y)
+// One thread per (n, oy, ox, 16-byte group of channels): every tap is one aligned 128-bit load of VEC channels, a warp reads
+// 512 contiguous bytes per tap, neighbouring outputs re-read their shared taps from L1/L2 - DRAM sees each input once.
+template <typename T>
+__global__ void __launch_bounds__(kThreads) k_upfirdn2d_cl(const UpfirdnParams p) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    __shared__ float s_w[kMaxTaps];
+    const int taps = p.fH * p.fW;
+    for (int i = threadIdx.x; i < taps; i += kThreads) {
+        const int ky = i / p.fW, kx = i - ky * p.fW;
+        const int sy = p.flip ? ky : p.fH - 1 - ky, sx = p.flip ? kx : p.fW - 1 - kx;
+        s_w[i] = p.f[sy * p.fsh + sx * p.fsw] * p.gain;
+    }
+    __syncthreads();
+    const T* xp = reinterpret_cast<const T*>(p.x);
+    T* yp = reinterpret_cast<T*>(p.y);
+    const unsigned cv = (unsigned)(p.C / VEC);
+    const unsigned total = (unsigned)p.N * (unsigned)p.outH * (unsigned)p.outW * cv;       // < 2^31 (checked by the launcher)
+    for (unsigned idx = blockIdx.x * kThreads + threadIdx.x; idx < total; idx += gridDim.x * kThreads) {
+        unsigned r = idx;
+        const int c = (int)(r % cv) * VEC; r /= cv;
+        const int ox = (int)(r % (unsigned)p.outW); r /= (unsigned)p.outW;
+        const int oy = (int)(r % (unsigned)p.outH);
+        const int n = (int)(r / (unsigned)p.outH);
+        const int ux0 = ox * p.downx - p.padx0, uy0 = oy * p.downy - p.pady0;
+        const int kx0 = pos_mod(-ux0, p.upx), ky0 = pos_mod(-uy0, p.upy);
+        const T* xi = xp + n * p.xs[0] + c;
+        float acc[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) acc[e] = 0.f;
+        for (int ky = ky0; ky < p.fH; ky += p.upy) {
+            const int iy = (uy0 + ky) / p.upy;
+            if (iy < 0 || iy >= p.inH) continue;
+            for (int kx = kx0; kx < p.fW; kx += p.upx) {
+                const int ix = (ux0 + kx) / p.upx;
+                if (ix < 0 || ix >= p.inW) continue;
+                const uint4 raw = __ldg(reinterpret_cast<const uint4*>(xi + iy * p.xs[2] + ix * p.xs[3]));
+                const T* v = reinterpret_cast<const T*>(&raw);
+                const float w = s_w[ky * p.fW + kx];
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) acc[e] = fmaf(Px<T>::ld(v[e]), w, acc[e]);
+            }
+        }
+        alignas(16) T out[VEC];
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) out[e] = Px<T>::st(acc[e]);
+        *reinterpret_cast<uint4*>(yp + n * p.ys[0] + c + oy * p.ys[2] + ox * p.ys[3]) = *reinterpret_cast<const uint4*>(out);
+    }
+}
+
+template <typename T>
+bool channels_last_ok(const UpfirdnParams& p) {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (sizeof(T) > 4 || p.xs[1] != 1 || p.ys[1] != 1 || p.C % VEC != 0 || p.fH * p.fW > kMaxTaps) return false;
+    const uintptr_t mask = 15;
+    if ((reinterpret_cast<uintptr_t>(p.x) & mask) || (reinterpret_cast<uintptr_t>(p.y) & mask)) return false;
+    for (int i : {0, 2, 3})
+        if (p.xs[i] % VEC != 0 || p.ys[i] % VEC != 0) return false;
+    return (long long)p.N * p.outH * p.outW * (p.C / VEC) < 0x7fffffffll;
+}
+
 template <typename T>
 int launch_upfirdn2d(UpfirdnParams p, cudaStream_t stream) {
     using S = typename Px<T>::acc;
@@ -417,6 +478,14 @@ int launch_upfirdn2d(UpfirdnParams p, cudaStream_t stream) {
     {
         const int rc = try_launch_fast<T>(p, n_sm, stream);
         if (rc <= 0) return rc;
+    }
+    if (channels_last_ok<T>(p)) {
+        const long long total = (long long)p.N * p.outH * p.outW * (p.C / (16 / (int)sizeof(T)));
+        const long long blocks = (total + kThreads - 1) / kThreads;
+        const int grid = (int)(blocks < (long long)n_sm * 32 ? blocks : (long long)n_sm * 32);
+        k_upfirdn2d_cl<T><<<grid, kThreads, 0, stream>>>(p);
+        P3D_LAUNCH_CHECK();
+        return P3D_OK;
     }
     // footprint of a 64x16 output tile in input pixels (+1 for the floor of the first index)
     p.inTileW = (kTileW * p.downx + p.fW - 1 + p.upx - 1) / p.upx + 1;

@@ -95,14 +95,34 @@ class PeerGather:
         total = slots * self.world * self.shard_bytes
         box = [None]
         ptr = C.c_void_p()
+        ok, why = 1, ''
         with torch.cuda.device(device):
-            if self.rank == dst:
-                handle = C.create_string_buffer(64)
-                _lib.check(L.p3d_ipc_alloc(total, C.byref(ptr), handle))
-                box[0] = handle.raw
+            # every rank goes through the same collectives whatever happens locally: a rank whose export / import fails (no peer
+            # access between two devices, IPC disabled in a container) reports it, and ALL ranks then fall back to the NCCL gather
+            try:
+                if self.rank == dst:
+                    handle = C.create_string_buffer(64)
+                    _lib.check(L.p3d_ipc_alloc(total, C.byref(ptr), handle))
+                    box[0] = handle.raw
+            except Exception as e:                                             # noqa: BLE001 - reported below, collectively
+                ok, why = 0, str(e)
             dist.broadcast_object_list(box, src=dst, group=group)
-            if self.rank != dst:
-                _lib.check(L.p3d_ipc_open(box[0], C.byref(ptr)))
+            try:
+                if self.rank != dst:
+                    if box[0] is None:
+                        raise RuntimeError('the consumer rank could not export its buffer')
+                    _lib.check(L.p3d_ipc_open(box[0], C.byref(ptr)))
+            except Exception as e:                                             # noqa: BLE001
+                ok, why = 0, str(e)
+            flag = torch.tensor([ok], device=device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if int(flag.item()) == 0:
+                if ptr.value:
+                    (L.p3d_ipc_free if self.rank == dst else L.p3d_ipc_close)(ptr.value)
+                self.p2p = False
+                import warnings
+                warnings.warn('PeerGather: peer-to-peer delivery unavailable (%s); using the NCCL gather' % (why or 'another rank failed'))
+                return
             self._base = int(ptr.value)
             if self.rank == dst:
                 self.buf = torch.as_tensor(_RawCuda(self._base, (slots, self.world) + self.shard_shape), device=device)

@@ -254,6 +254,26 @@ def test_upfirdn2d_fast_path_misaligned_rows_and_views(kw, dtype, tol):
         assert (y.cpu().double() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize('dtype,tol', [(torch.float32, 2e-5), (torch.float16, 2e-3), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize('kw', [dict(padding=[1, 1, 1, 1], gain=4.0), dict(up=2, padding=[2, 1, 2, 1], gain=4.0), dict(down=2, padding=[1, 1, 1, 1]),
+                                dict(up=2, down=3, padding=[4, -1, 0, 5], flip_filter=True)], ids=['blur', 'up2', 'down2', 'up2_down3_crop_flip'])
+def test_upfirdn2d_channels_last_vector_kernel(kw, dtype, tol):
+    """channels_last tensors whose channel count fills whole 16-byte groups take the vectorised kernel (one 128-bit load of 4 / 8
+    channels per tap): odd image sizes, a non-symmetric 2-D filter, and a channels_last VIEW (batch slice) of a larger buffer."""
+    up = _up()
+    g = torch.Generator().manual_seed(13)
+    f = torch.rand(4, 4, generator=g) + 0.1
+    big = torch.randn(3, 32, 37, 53, generator=g).to(dtype)
+    xcl = big.to(DEV).contiguous(memory_format=torch.channels_last)
+    for view, xv in ((big, xcl), (big[1:3], xcl[1:3])):
+        assert xv.stride(1) == 1
+        y = up.upfirdn2d(xv, f.to(DEV), **kw)
+        ref = oo.upfirdn2d(view.double(), f.double(), up=kw.get('up', 1), down=kw.get('down', 1), padding=kw['padding'],
+                           flip_filter=kw.get('flip_filter', False), gain=kw.get('gain', 1))
+        assert y.shape == ref.shape and y.dtype == dtype and y.stride(1) == 1
+        assert (y.cpu().double() - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
 # ------------------------------------------------------------------------------------------ filtered_lrelu
 def _fl():
     from panic3d_b200.torch_utils.ops import filtered_lrelu
