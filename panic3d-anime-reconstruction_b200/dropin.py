@@ -57,6 +57,23 @@ def install(renderer: bool = True, ops: bool = True, strict: bool = False):
     return done
 
 
+def install_paste(module=None):
+    """Rebind the reference's ``paste_front`` (``training/triplane.py:608-691``) and its two render helpers
+    to the fused implementation in ``panic3d_b200.paste``.  ``G.f`` looks ``paste_front`` up in its own module's globals
+    at call time (triplane.py:498-502), so setting the attribute on that module is the whole plug-in: no caller edits.
+    ``module``: the reference's already-imported ``training.triplane`` (default: import it by that name).
+    Returns the names that were rebound."""
+    from . import paste
+    if module is None:
+        module = importlib.import_module('training.triplane')
+    names = ['paste_front', 'get_front_occlusion', 'get_front_weights']
+    for name in names:
+        if not hasattr(module, '_p3d_reference_' + name):
+            setattr(module, '_p3d_reference_' + name, getattr(module, name, None))       # keep the original reachable for A/B runs
+        setattr(module, name, getattr(paste, name))
+    return names
+
+
 def patch_generator(G):
     """For a TriPlaneGenerator that was built BEFORE install() (e.g. unpickled): swap its two hot-path
     sub-modules in place.  Both are parameter-free, so no weights move."""
