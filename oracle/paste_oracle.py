@@ -31,7 +31,7 @@ def sobel_magnitude(x, eps=1e-6):
     """kornia.filters.sobel(x, normalized=True, eps=1e-6) for x (B,C,H,W): per-channel gradient magnitude."""
     b, c, h, w = x.shape
     kx = torch.tensor([[-1., 0., 1.], [-2., 0., 2.], [-1., 0., 1.]], dtype=x.dtype) / 8
-    k = torch.stack([kx, kx.t()])[:, None]                                   # (2,1,3,3): d/dx, d/dy; conv = cross-correlation
+    k = torch.stack([kx, kx.t()])[:, None].to(x.device)                                   # (2,1,3,3): d/dx, d/dy; conv = cross-correlation
     g = F.conv2d(F.pad(x.reshape(b * c, 1, h, w), [1, 1, 1, 1], mode='replicate'), k).view(b, c, 2, h, w)
     return torch.sqrt(g[:, :, 0] * g[:, :, 0] + g[:, :, 1] * g[:, :, 1] + eps)
 

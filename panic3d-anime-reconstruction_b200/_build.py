@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(out)
     os.makedirs(os.path.dirname(LIB), exist_ok=True)       # lib/ holds only ignored artefacts: a fresh clone has no such directory
     tmp = LIB + '.tmp.%d' % os.getpid()
-    r = subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', tmp] + objs,
+    r = subprocess.run([nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', tmp] + objs + ['-lz'],     # zlib: deflate + crc32 of the PNG writer (csrc/image_io.cu)
                        stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)

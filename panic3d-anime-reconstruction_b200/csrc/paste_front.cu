@@ -18,7 +18,7 @@ struct PasteArgs {
     const float *image, *xyz, *wts, *front, *occ, *ro, *rd, *eroded;
     float *o_image, *o_paste, *o_mask, *o_parts;
     int N, R, S, Rf, normalize;
-    float bw, half_bw;
+    float inv_bw, half_bw;
     float t_w, t_e, t_o, t_d;
     float scale;       // (float)R / S : torch's area_pixel_compute_scale for size-given interpolate
 };
@@ -46,11 +46,11 @@ __device__ __forceinline__ float bilerp(const float* __restrict__ img, int R, Li
 // sample_orthofront's grid coordinate of one world coordinate (triplane.py:557,560), then grid_sample's
 // un-normalisation (align_corners=False) and border clipping (aten GridSampler.h)
 struct Tap { int i0; float f; float gmul; };     // floor index, fraction, d(index)/d(world coordinate) (0 where clipped)
-__device__ __forceinline__ Tap ortho_tap(float v, float half_bw, float bw, int size) {
-    float vij = 1.f - (v + half_bw) / bw;
+__device__ __forceinline__ Tap ortho_tap(float v, float half_bw, float inv_bw, int size) {
+    float vij = 1.f - (v + half_bw) * inv_bw;            // torch's CUDA div-by-scalar multiplies by the reciprocal
     float g = vij * 2.f - 1.f;
-    float ix = ((g + 1.f) * (float)size - 1.f) / 2.f;
-    float mul = (float)size * 0.5f * (-2.f / bw);
+    float ix = ((g + 1.f) * (float)size - 1.f) * 0.5f;
+    float mul = -(float)size * inv_bw;
     float hi = (float)(size - 1);
     if (ix <= 0.f) { ix = 0.f; mul = 0.f; }
     else if (ix >= hi) { ix = hi; mul = 0.f; }
@@ -65,25 +65,36 @@ __device__ __forceinline__ Tap ortho_tap(float v, float half_bw, float bw, int s
 // ---------------------------------------------------------------- forward
 __global__ void __launch_bounds__(NT) k_paste_front(PasteArgs a) {
     __shared__ float s_up[3][TH + 2][TW + 2 + 1];
+    __shared__ Lin s_row[TH + 2], s_col[TW + 2];          // source rows / columns + weights of the tile's halo, computed once
     const int n = blockIdx.z, tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
     const int R = a.R, S = a.S;
     const float* xyz = a.xyz + (size_t)n * 3 * R * R;
+    if (threadIdx.x < TH + 2) s_row[threadIdx.x] = lin_src(min(max(ty0 + (int)threadIdx.x - 1, 0), S - 1), a.scale, R);   // replicate pad
+    else if (threadIdx.x >= 64 && threadIdx.x < 64 + TW + 2) s_col[threadIdx.x - 64] = lin_src(min(max(tx0 + (int)threadIdx.x - 65, 0), S - 1), a.scale, R);
+    __syncthreads();
     for (int idx = threadIdx.x; idx < (TH + 2) * (TW + 2); idx += NT) {
         int hy = idx / (TW + 2), hx = idx - hy * (TW + 2);
-        int oy = min(max(ty0 + hy - 1, 0), S - 1), ox = min(max(tx0 + hx - 1, 0), S - 1);     // replicate pad of the Sobel
-        Lin ly = lin_src(oy, a.scale, R), lx = lin_src(ox, a.scale, R);
+        const Lin ly = s_row[hy], lx = s_col[hx];
+        const float* r0 = xyz + ly.i0 * R, *r1 = xyz + ly.i1 * R;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) s_up[c][hy][hx] = bilerp(xyz + c * R * R, R, ly, lx);
+        for (int c = 0; c < 3; ++c) {
+            float v0 = lx.l0 * __ldg(r0 + c * R * R + lx.i0) + lx.l1 * __ldg(r0 + c * R * R + lx.i1);
+            float v1 = lx.l0 * __ldg(r1 + c * R * R + lx.i0) + lx.l1 * __ldg(r1 + c * R * R + lx.i1);
+            s_up[c][hy][hx] = ly.l0 * v0 + ly.l1 * v1;
+        }
     }
     __syncthreads();
     const int lx_ = threadIdx.x & (TW - 1), ly_ = threadIdx.x / TW;
     const int ox = tx0 + lx_, oy = ty0 + ly_;
     if (ox >= S || oy >= S) return;
-    const size_t pix = (size_t)oy * S + ox, plane = (size_t)S * S;
-    const Lin by = lin_src(oy, a.scale, R), bx = lin_src(ox, a.scale, R);
+    // 32-bit offsets inside one view (the host checks 5 * N * S * S < 2^31): one IMAD.WIDE per access instead of 64-bit chains
+    const int pix = oy * S + ox, plane = S * S;
+    const Lin by = s_row[ly_ + 1], bx = s_col[lx_ + 1];
+    const int o00 = by.i0 * R + bx.i0, o01 = by.i0 * R + bx.i1, o10 = by.i1 * R + bx.i0, o11 = by.i1 * R + bx.i1;
 
     // mask 1: visible weights (triplane.py:625-629)
-    float qw = bilerp(a.wts + (size_t)n * R * R, R, by, bx);
+    const float* wv = a.wts + (size_t)n * R * R;
+    float qw = by.l0 * (bx.l0 * __ldg(wv + o00) + bx.l1 * __ldg(wv + o01)) + by.l1 * (bx.l0 * __ldg(wv + o10) + bx.l1 * __ldg(wv + o11));
     float wmask = qw > a.t_w ? 1.f : 0.f;
 
     // mask 2: deep crevasses - normalised Sobel magnitude of the up-sampled xyz, L2 norm over channels (:632-637)
@@ -102,8 +113,8 @@ __global__ void __launch_bounds__(NT) k_paste_front(PasteArgs a) {
     float fmask;
     {
         const float* o = a.occ + (size_t)n * R * R;
-        float v00 = __ldg(o + by.i0 * R + bx.i0) < a.t_o ? 1.f : 0.f, v01 = __ldg(o + by.i0 * R + bx.i1) < a.t_o ? 1.f : 0.f;
-        float v10 = __ldg(o + by.i1 * R + bx.i0) < a.t_o ? 1.f : 0.f, v11 = __ldg(o + by.i1 * R + bx.i1) < a.t_o ? 1.f : 0.f;
+        float v00 = __ldg(o + o00) < a.t_o ? 1.f : 0.f, v01 = __ldg(o + o01) < a.t_o ? 1.f : 0.f;
+        float v10 = __ldg(o + o10) < a.t_o ? 1.f : 0.f, v11 = __ldg(o + o11) < a.t_o ? 1.f : 0.f;
         fmask = by.l0 * (bx.l0 * v00 + bx.l1 * v01) + by.l1 * (bx.l0 * v10 + bx.l1 * v11);
     }
 
@@ -113,11 +124,12 @@ __global__ void __launch_bounds__(NT) k_paste_front(PasteArgs a) {
     float dmask;
     {
         int sy = min((int)floorf((float)oy * a.scale), R - 1), sx = min((int)floorf((float)ox * a.scale), R - 1);
-        size_t o = (size_t)n * 3 * R * R + (size_t)sy * R + sx, st = (size_t)R * R;
-        float d0 = __fsub_rn(-__ldg(a.xyz + o), __ldg(a.ro + o));
-        float d1 = __fsub_rn(__ldg(a.xyz + o + st), __ldg(a.ro + o + st));
-        float d2 = __fsub_rn(-__ldg(a.xyz + o + 2 * st), __ldg(a.ro + o + 2 * st));
-        float n0 = __ldg(a.rd + o), n1 = __ldg(a.rd + o + st), n2 = __ldg(a.rd + o + 2 * st);
+        const int o = sy * R + sx, st = R * R;
+        const float* ro = a.ro + (size_t)n * 3 * R * R, *rd = a.rd + (size_t)n * 3 * R * R;
+        float d0 = __fsub_rn(-__ldg(xyz + o), __ldg(ro + o));
+        float d1 = __fsub_rn(__ldg(xyz + o + st), __ldg(ro + o + st));
+        float d2 = __fsub_rn(-__ldg(xyz + o + 2 * st), __ldg(ro + o + 2 * st));
+        float n0 = __ldg(rd + o), n1 = __ldg(rd + o + st), n2 = __ldg(rd + o + 2 * st);
         float dot = __fadd_rn(__fadd_rn(__fmul_rn(d0, n0), __fmul_rn(d1, n1)), __fmul_rn(d2, n2));
         float r0 = __fsub_rn(d0, __fmul_rn(dot, n0)), r1 = __fsub_rn(d1, __fmul_rn(dot, n1)), r2 = __fsub_rn(d2, __fmul_rn(dot, n2));
         float q = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r0, r0), __fmul_rn(r1, r1)), __fmul_rn(r2, r2)));
@@ -130,7 +142,7 @@ __global__ void __launch_bounds__(NT) k_paste_front(PasteArgs a) {
     // mask 5: eroded front weights looked up the same way (:648-662); 1 when front_weight_erosion < 1
     float fwmask = 1.f;
     if (a.Rf > 0) {
-        Tap tr = ortho_tap(vy, a.half_bw, a.bw, a.Rf), tc = ortho_tap(vx, a.half_bw, a.bw, a.Rf);
+        Tap tr = ortho_tap(vy, a.half_bw, a.inv_bw, a.Rf), tc = ortho_tap(vx, a.half_bw, a.inv_bw, a.Rf);
         const float* e = a.eroded + (size_t)n * a.Rf * a.Rf;
         int r1 = min(tr.i0 + 1, a.Rf - 1), c1 = min(tc.i0 + 1, a.Rf - 1);         // weight is 0 where the neighbour is outside
         float nw = (1.f - tr.f) * (1.f - tc.f), ne = tr.f * (1.f - tc.f), sw = (1.f - tr.f) * tc.f, se = tr.f * tc.f;
@@ -140,27 +152,30 @@ __global__ void __launch_bounds__(NT) k_paste_front(PasteArgs a) {
     const float mask = wmask * smask * fmask * dmask * fwmask;
 
     // paste + blend (:670-679); torch.lerp's two-sided formula
-    Tap tr = ortho_tap(vy, a.half_bw, a.bw, S), tc = ortho_tap(vx, a.half_bw, a.bw, S);
+    Tap tr = ortho_tap(vy, a.half_bw, a.inv_bw, S), tc = ortho_tap(vx, a.half_bw, a.inv_bw, S);
     int r1 = min(tr.i0 + 1, S - 1), c1 = min(tc.i0 + 1, S - 1);
     float nw = (1.f - tr.f) * (1.f - tc.f), ne = tr.f * (1.f - tc.f), sw = (1.f - tr.f) * tc.f, se = tr.f * tc.f;
+    const size_t view3 = (size_t)n * 3 * plane;
+    const float* fv = a.front + view3, *iv = a.image + view3;
+    float* opv = a.o_paste + view3, *oiv = a.o_image + view3;
+    const int t00 = tr.i0 * S + tc.i0, t10 = r1 * S + tc.i0, t01 = tr.i0 * S + c1, t11 = r1 * S + c1;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float* f = a.front + ((size_t)n * 3 + c) * plane;
-        float f00 = __ldg(f + (size_t)tr.i0 * S + tc.i0), f10 = __ldg(f + (size_t)r1 * S + tc.i0);
-        float f01 = __ldg(f + (size_t)tr.i0 * S + c1), f11 = __ldg(f + (size_t)r1 * S + c1);
+        const float* f = fv + c * plane;
+        float f00 = __ldg(f + t00), f10 = __ldg(f + t10), f01 = __ldg(f + t01), f11 = __ldg(f + t11);
         if (a.normalize) { f00 = f00 * 2.f - 1.f; f10 = f10 * 2.f - 1.f; f01 = f01 * 2.f - 1.f; f11 = f11 * 2.f - 1.f; }
         float paste = f00 * nw + f10 * ne + f01 * sw + f11 * se;
-        size_t o = ((size_t)n * 3 + c) * plane + pix;
-        float img = __ldg(a.image + o);
+        const int o = c * plane + pix;
+        float img = __ldg(iv + o);
         float diff = paste - img;
-        a.o_paste[o] = paste;
-        a.o_image[o] = mask < 0.5f ? img + mask * diff : paste - diff * (1.f - mask);
+        opv[o] = paste;
+        oiv[o] = mask < 0.5f ? img + mask * diff : paste - diff * (1.f - mask);
     }
     a.o_mask[(size_t)n * plane + pix] = mask;
     if (a.o_parts) {
-        size_t st = (size_t)a.N * plane, o = (size_t)n * plane + pix;
-        a.o_parts[o] = wmask; a.o_parts[st + o] = smask; a.o_parts[2 * st + o] = fmask; a.o_parts[3 * st + o] = dmask;
-        a.o_parts[4 * st + o] = fwmask;
+        float* pv = a.o_parts + (size_t)n * plane;
+        const int st = a.N * plane;                                 // 5 * N * S * S < 2^31 (checked by the host)
+        pv[pix] = wmask; pv[st + pix] = smask; pv[2 * st + pix] = fmask; pv[3 * st + pix] = dmask; pv[4 * st + pix] = fwmask;
     }
 }
 
@@ -169,7 +184,7 @@ struct PasteBwdArgs {
     const float *xyz, *front, *mask, *g_image, *g_paste;
     float *d_image, *d_xyz;
     int N, R, S, normalize;
-    float bw, half_bw, scale;
+    float inv_bw, half_bw, scale;
 };
 
 __global__ void __launch_bounds__(NT) k_paste_front_bwd(PasteBwdArgs a) {
@@ -190,7 +205,7 @@ __global__ void __launch_bounds__(NT) k_paste_front_bwd(PasteBwdArgs a) {
     const Lin by = lin_src(oy, a.scale, R), bx = lin_src(ox, a.scale, R);
     const float* xyz = a.xyz + (size_t)n * 3 * R * R;
     const float vx = bilerp(xyz, R, by, bx), vy = bilerp(xyz + R * R, R, by, bx);
-    Tap tr = ortho_tap(vy, a.half_bw, a.bw, S), tc = ortho_tap(vx, a.half_bw, a.bw, S);
+    Tap tr = ortho_tap(vy, a.half_bw, a.inv_bw, S), tc = ortho_tap(vx, a.half_bw, a.inv_bw, S);
     int r1 = min(tr.i0 + 1, S - 1), c1 = min(tc.i0 + 1, S - 1);
     float g_r = 0.f, g_c = 0.f;                                    // d loss / d (row index), d (column index)
 #pragma unroll
@@ -252,6 +267,8 @@ int check_params(const p3d_paste_params* p) {
                 p->res_render, p->res_image, p->res_front);
     P3D_REQUIRE(p->res_image <= 16384 && p->res_render <= 16384 && p->res_front <= 16384, "p3d_paste: resolution above 16384");
     P3D_REQUIRE(p->box_warp > 0, "p3d_paste: box_warp must be positive");
+    P3D_REQUIRE(5ll * p->n_views * p->res_image * p->res_image < (1ll << 31) && 3ll * p->n_views * p->res_render * p->res_render < (1ll << 31),
+                "p3d_paste: batch too large for 32-bit offsets (N=%d S=%d R=%d): split the views", p->n_views, p->res_image, p->res_render);
     return P3D_OK;
 }
 
@@ -295,7 +312,7 @@ extern "C" int p3d_paste_front(const p3d_paste_params* p, const float* image, co
     a.ro = ray_origins; a.rd = ray_dirs; a.eroded = front_eroded;
     a.o_image = out_image; a.o_paste = out_paste; a.o_mask = out_mask; a.o_parts = out_parts;
     a.N = p->n_views; a.R = p->res_render; a.S = p->res_image; a.Rf = p->res_front; a.normalize = p->normalize_images;
-    a.bw = (float)p->box_warp; a.half_bw = (float)(p->box_warp / 2);
+    a.inv_bw = 1.f / (float)p->box_warp; a.half_bw = (float)(p->box_warp / 2);
     a.t_w = (float)p->thresh_weight; a.t_e = (float)p->thresh_edges; a.t_o = (float)p->thresh_occ; a.t_d = (float)p->thresh_dxyz;
     a.scale = (float)p->res_render / (float)p->res_image;
     dim3 grd((a.S + TW - 1) / TW, (a.S + TH - 1) / TH, a.N);
@@ -313,7 +330,7 @@ extern "C" int p3d_paste_front_backward(const p3d_paste_params* p, const float* 
     a.xyz = image_xyz; a.front = front_rgb; a.mask = mask; a.g_image = g_image; a.g_paste = g_paste;
     a.d_image = d_image; a.d_xyz = d_xyz;
     a.N = p->n_views; a.R = p->res_render; a.S = p->res_image; a.normalize = p->normalize_images;
-    a.bw = (float)p->box_warp; a.half_bw = (float)(p->box_warp / 2);
+    a.inv_bw = 1.f / (float)p->box_warp; a.half_bw = (float)(p->box_warp / 2);
     a.scale = (float)p->res_render / (float)p->res_image;
     dim3 grd((a.S + TW - 1) / TW, (a.S + TH - 1) / TH, a.N);
     k_paste_front_bwd<<<grd, NT, 0, (cudaStream_t)stream>>>(a);

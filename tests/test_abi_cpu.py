@@ -29,7 +29,7 @@ def header_functions():
 def test_every_declared_symbol_is_exported(lib):
     from panic3d_b200 import _lib
     from panic3d_b200.torch_utils.ops import bias_act, upfirdn2d, filtered_lrelu   # noqa: F401  (register their prototypes)
-    from panic3d_b200 import paste                                                 # noqa: F401
+    from panic3d_b200 import paste, imageio                                        # noqa: F401
     declared = header_functions()
     assert len(declared) >= 10
     for name in declared:
