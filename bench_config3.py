@@ -3,7 +3,9 @@
 perspective views of one subject through `G.f`, super-resolution head on) on a synthetic-weight TriPlaneGenerator built
 with the training configuration's kwargs (`_train/eg3dc/trainers/train_eclustrousC.py:339-343,409-440,479-480`) and the eval
 loader's settings (`_train/eg3dc/util/eg3dc_v0.py:24-56`: 96+96 samples, force_sigmoid; `generate.py:53-57`: crop 0.1,
-cull 0.5; `paste_params=None` - kornia is not in this image).
+cull 0.5).  `--paste` adds the eval script's `paste_params` (`generate.py:59-65`): every view then runs `paste_front`
+- the reference's own (its two kornia calls served by the restatement in oracle/paste_oracle.py: kornia is not in this image) in the
+reference arm, `panic3d_b200.paste` rebound by `dropin.install_paste()` in ours - including its second render from the visible surface.
 
 Two arms, one process each (module identity is decided at import time), same weights (same seed, same construction order):
 
@@ -97,12 +99,14 @@ def main():
     ap.add_argument('--tiny', action='store_true', help='small channels / 16x16 rays (CPU smoke test of the harness)')
     ap.add_argument('--device', default='cuda:0')
     ap.add_argument('--reps', type=int, default=2, help='timed repetitions of the 16-view sweep')
+    ap.add_argument('--paste', action='store_true', help="run the sweep with the eval script's paste_params (generate.py:59-65)")
     args = ap.parse_args()
     import torch
     if args.compare:
         a, b = (torch.load(f) for f in args.compare)
         rep = {'arms': [a['arm'], b['arm']], 'views': len(a['views'])}
-        for key in ('image_raw', 'image', 'image_depth', 'image_weights', 'feature_image'):
+        for key in ('image_raw', 'image', 'image_depth', 'image_weights', 'feature_image', 'image_prepaste', 'paste', 'mask', 'mask_weights',
+                    'mask_edges', 'mask_occ', 'mask_dxyz'):
             if key in a and key in b:
                 d = (a[key].float() - b[key].float()).abs()
                 rep[key] = {'max_abs': float(d.max()), 'mean_abs': float(d.mean()), 'frac_within_1e-3': float((d < 1e-3).float().mean()),
@@ -110,6 +114,16 @@ def main():
         rep['note'] = ('cull_clouds = 0.5 is a hard threshold on sigma (renderer.py:150-153): a sample within rounding of it flips in one arm, '
                        'so isolated rays differ by more than 1e-3 (same criterion as the cull fixtures in tests/test_render_gpu.py); the '
                        '512^2 image goes through the fp16 super-resolution head')
+        if 'mask' in a and 'mask' in b:
+            # thresh_dxyz = 5e-6 sits at the rounding level of the rendered xyz (|xyz| ~ 0.3, ulp 3e-8; the two renderers agree to ~1e-6):
+            # mask_dxyz is decided by noise in EITHER implementation, so the pasted image is compared where the masks agree
+            same = ((a['mask'] - b['mask']).abs() < 1e-3)
+            d = (a['image'].float() - b['image'].float()).abs()
+            rep['paste'] = {'mask_agreement': float(same.float().mean()), 'mask_mean': [float(a['mask'].mean()), float(b['mask'].mean())],
+                            'image_max_abs_where_masks_agree': float(d[same.expand_as(d)].max()),
+                            'image_mean_abs_where_masks_agree': float(d[same.expand_as(d)].mean())}
+            for k in ('mask_weights', 'mask_edges', 'mask_occ', 'mask_dxyz'):
+                rep['paste'][k + '_agreement'] = float(((a[k] - b[k]).abs() < 1e-3).float().mean())
         rep['views_per_s'] = {a['arm']: a['views_per_s'], b['arm']: b['views_per_s']}
         rep['speedup'] = b['views_per_s'] / a['views_per_s'] if a['arm'] == 'reference' else a['views_per_s'] / b['views_per_s']
         print(json.dumps(rep))
@@ -118,10 +132,16 @@ def main():
     from baseline import ref_env
     ref_env.setup()
     dev = torch.device(args.device)
+    if args.paste and args.arm == 'reference':
+        from oracle.paste_oracle import kornia_shim                 # reference arm only: the two kornia calls of ITS paste_front
+        k = kornia_shim()
+        sys.modules['kornia'], sys.modules['kornia.filters'], sys.modules['kornia.morphology'] = k, k.filters, k.morphology
     if args.arm == 'ours':
         import panic3d_b200.dropin as dropin
         installed = dropin.install()
     import training.triplane as tp
+    if args.paste and args.arm == 'ours':
+        dropin.install_paste(tp)
     mod_file = sys.modules[tp.ImportanceRenderer.__module__].__file__
     assert ('baseline/_ref' in mod_file.replace(os.sep, '/')) == (args.arm == 'reference'), mod_file
     G, R = build_generator(args, torch)
@@ -137,9 +157,19 @@ def main():
              'triplane_crop': 0.1, 'cull_clouds': 0.5}
         if ws is not None:
             x['ws'] = ws
+        if args.paste:
+            x['cond'] = {'image_ortho_front': front}
+            x['paste_params'] = {'mode': 'default', 'thresh_weight': 0.95, 'thresh_edges': 0.02, 'thresh_occ': 0.05, 'offset_occ': 0.01,
+                                 'thresh_dxyz': 0.000005}
         return x
 
+    res_img = 512                                              # the SR head always outputs img_resolution = 512
+    front = torch.rand(1, 3, res_img, res_img, generator=torch.Generator().manual_seed(7)).to(dev)
+
     outs = {k: [] for k in ('image_raw', 'image', 'image_depth', 'image_weights')}
+    pouts = {k: [] for k in ('paste', 'mask', 'mask_weights', 'mask_edges', 'mask_occ', 'mask_dxyz')} if args.paste else {}
+    if args.paste:
+        outs['image_prepaste'] = []
     syn_fwd = G.backbone.synthesis.forward                      # an nn.Module: patch its forward on the instance
     with torch.no_grad():
         # ---- parity pass
@@ -150,7 +180,7 @@ def main():
             u_f = torch.rand(R * R, Sf, generator=gen)
             x = xin_for(e, a, f)
             if args.arm == 'reference':
-                with InjectRand(torch, [u_c, u_f]):
+                with InjectRand(torch, [u_c, u_f] * (2 if args.paste else 1)):   # paste_front renders a second time: same jitter again
                     out = G.f(x)
             else:
                 G.renderer.injected_noise = (u_c, u_f)
@@ -159,6 +189,8 @@ def main():
             ws = x['ws']
             for k in outs:
                 outs[k].append(out[k].float().cpu())
+            for k in pouts:
+                pouts[k].append(out['paste'][k].float().cpu())
         G.backbone.synthesis.forward = syn_fwd
         # ---- timing pass: the sweep as generate.py runs it
         if dev.type == 'cuda':
@@ -177,12 +209,12 @@ def main():
                 G.f(xin_for(e, a, f))
             dt = (time.perf_counter() - t0) * len(views) / 2 * args.reps
     vps = args.reps * len(views) / dt
-    res = {k: torch.cat(v) for k, v in outs.items()}
+    res = {k: torch.cat(v) for k, v in {**outs, **pouts}.items()}
     res.update(arm=args.arm, views=views, views_per_s=vps, plane=args.plane)
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
         torch.save(res, args.out)
-    line = {'config': 'BASELINE configs[2]: G.f 16-view sweep, SR on, synthetic weights', 'arm': args.arm, 'views_per_s': vps,
+    line = {'config': 'BASELINE configs[2]: G.f 16-view sweep, SR on, synthetic weights' + (', paste_params on' if args.paste else ''), 'arm': args.arm, 'views_per_s': vps,
             'ms_per_view': 1e3 / vps, 'plane': args.plane, 'rays': R * R, 'samples': [S, Sf],
             'renderer_module': mod_file.replace(ROOT, '.'), 'image_mean': float(res['image'].mean())}
     if args.arm == 'ours':

@@ -25,14 +25,14 @@ struct PasteArgs {
 
 // F.interpolate(mode='bilinear', align_corners=False): source index / weights of one output coordinate
 // (aten UpSample.h: area_pixel_compute_source_index + guard_index_and_lambda)
-struct Lin { int i0, i1; float l0, l1; };
+struct Lin { unsigned i0, i1; float l0, l1; };   // unsigned: a 32-bit offset folds into one IMAD.WIDE.U32 per access
 __device__ __forceinline__ Lin lin_src(int dst, float scale, int in) {
     float s = scale * ((float)dst + 0.5f) - 0.5f;
     s = s < 0.f ? 0.f : s;
     int i0 = min((int)s, in - 1);
     Lin r;
-    r.i0 = i0;
-    r.i1 = min(i0 + 1, in - 1);
+    r.i0 = (unsigned)i0;
+    r.i1 = (unsigned)min(i0 + 1, in - 1);
     r.l1 = fminf(fmaxf(s - (float)i0, 0.f), 1.f);
     r.l0 = 1.f - r.l1;
     return r;
@@ -45,7 +45,7 @@ __device__ __forceinline__ float bilerp(const float* __restrict__ img, int R, Li
 
 // sample_orthofront's grid coordinate of one world coordinate (triplane.py:557,560), then grid_sample's
 // un-normalisation (align_corners=False) and border clipping (aten GridSampler.h)
-struct Tap { int i0; float f; float gmul; };     // floor index, fraction, d(index)/d(world coordinate) (0 where clipped)
+struct Tap { unsigned i0; float f; float gmul; };     // floor index, fraction, d(index)/d(world coordinate) (0 where clipped)
 __device__ __forceinline__ Tap ortho_tap(float v, float half_bw, float inv_bw, int size) {
     float vij = 1.f - (v + half_bw) * inv_bw;            // torch's CUDA div-by-scalar multiplies by the reciprocal
     float g = vij * 2.f - 1.f;
@@ -56,7 +56,7 @@ __device__ __forceinline__ Tap ortho_tap(float v, float half_bw, float inv_bw, i
     else if (ix >= hi) { ix = hi; mul = 0.f; }
     Tap t;
     float fl = floorf(ix);
-    t.i0 = (int)fl;
+    t.i0 = (unsigned)(int)fl;
     t.f = ix - fl;
     t.gmul = mul;
     return t;
@@ -67,30 +67,31 @@ __global__ void __launch_bounds__(NT) k_paste_front(PasteArgs a) {
     __shared__ float s_up[3][TH + 2][TW + 2 + 1];
     __shared__ Lin s_row[TH + 2], s_col[TW + 2];          // source rows / columns + weights of the tile's halo, computed once
     const int n = blockIdx.z, tx0 = blockIdx.x * TW, ty0 = blockIdx.y * TH;
-    const int R = a.R, S = a.S;
+    const unsigned R = a.R, S = a.S;
     const float* xyz = a.xyz + (size_t)n * 3 * R * R;
-    if (threadIdx.x < TH + 2) s_row[threadIdx.x] = lin_src(min(max(ty0 + (int)threadIdx.x - 1, 0), S - 1), a.scale, R);   // replicate pad
-    else if (threadIdx.x >= 64 && threadIdx.x < 64 + TW + 2) s_col[threadIdx.x - 64] = lin_src(min(max(tx0 + (int)threadIdx.x - 65, 0), S - 1), a.scale, R);
+    if (threadIdx.x < TH + 2) s_row[threadIdx.x] = lin_src(min(max(ty0 + (int)threadIdx.x - 1, 0), a.S - 1), a.scale, a.R);   // replicate pad
+    else if (threadIdx.x >= 64 && threadIdx.x < 64 + TW + 2) s_col[threadIdx.x - 64] = lin_src(min(max(tx0 + (int)threadIdx.x - 65, 0), a.S - 1), a.scale, a.R);
     __syncthreads();
     for (int idx = threadIdx.x; idx < (TH + 2) * (TW + 2); idx += NT) {
         int hy = idx / (TW + 2), hx = idx - hy * (TW + 2);
         const Lin ly = s_row[hy], lx = s_col[hx];
-        const float* r0 = xyz + ly.i0 * R, *r1 = xyz + ly.i1 * R;
+        const unsigned h00 = ly.i0 * R + lx.i0, h01 = ly.i0 * R + lx.i1, h10 = ly.i1 * R + lx.i0, h11 = ly.i1 * R + lx.i1;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float v0 = lx.l0 * __ldg(r0 + c * R * R + lx.i0) + lx.l1 * __ldg(r0 + c * R * R + lx.i1);
-            float v1 = lx.l0 * __ldg(r1 + c * R * R + lx.i0) + lx.l1 * __ldg(r1 + c * R * R + lx.i1);
+        for (unsigned c = 0; c < 3; ++c) {
+            const float* pc = xyz + c * R * R;
+            float v0 = lx.l0 * __ldg(pc + h00) + lx.l1 * __ldg(pc + h01);
+            float v1 = lx.l0 * __ldg(pc + h10) + lx.l1 * __ldg(pc + h11);
             s_up[c][hy][hx] = ly.l0 * v0 + ly.l1 * v1;
         }
     }
     __syncthreads();
     const int lx_ = threadIdx.x & (TW - 1), ly_ = threadIdx.x / TW;
-    const int ox = tx0 + lx_, oy = ty0 + ly_;
+    const unsigned ox = tx0 + lx_, oy = ty0 + ly_;
     if (ox >= S || oy >= S) return;
     // 32-bit offsets inside one view (the host checks 5 * N * S * S < 2^31): one IMAD.WIDE per access instead of 64-bit chains
-    const int pix = oy * S + ox, plane = S * S;
+    const unsigned pix = oy * S + ox, plane = S * S;
     const Lin by = s_row[ly_ + 1], bx = s_col[lx_ + 1];
-    const int o00 = by.i0 * R + bx.i0, o01 = by.i0 * R + bx.i1, o10 = by.i1 * R + bx.i0, o11 = by.i1 * R + bx.i1;
+    const unsigned o00 = by.i0 * R + bx.i0, o01 = by.i0 * R + bx.i1, o10 = by.i1 * R + bx.i0, o11 = by.i1 * R + bx.i1;
 
     // mask 1: visible weights (triplane.py:625-629)
     const float* wv = a.wts + (size_t)n * R * R;
@@ -123,8 +124,8 @@ __global__ void __launch_bounds__(NT) k_paste_front(PasteArgs a) {
     // (no fma contraction), in the order the eager ops apply them.
     float dmask;
     {
-        int sy = min((int)floorf((float)oy * a.scale), R - 1), sx = min((int)floorf((float)ox * a.scale), R - 1);
-        const int o = sy * R + sx, st = R * R;
+        const unsigned sy = min((unsigned)(int)floorf((float)oy * a.scale), R - 1), sx = min((unsigned)(int)floorf((float)ox * a.scale), R - 1);
+        const unsigned o = sy * R + sx, st = R * R;
         const float* ro = a.ro + (size_t)n * 3 * R * R, *rd = a.rd + (size_t)n * 3 * R * R;
         float d0 = __fsub_rn(-__ldg(xyz + o), __ldg(ro + o));
         float d1 = __fsub_rn(__ldg(xyz + o + st), __ldg(ro + o + st));
@@ -132,7 +133,8 @@ __global__ void __launch_bounds__(NT) k_paste_front(PasteArgs a) {
         float n0 = __ldg(rd + o), n1 = __ldg(rd + o + st), n2 = __ldg(rd + o + 2 * st);
         float dot = __fadd_rn(__fadd_rn(__fmul_rn(d0, n0), __fmul_rn(d1, n1)), __fmul_rn(d2, n2));
         float r0 = __fsub_rn(d0, __fmul_rn(dot, n0)), r1 = __fsub_rn(d1, __fmul_rn(dot, n1)), r2 = __fsub_rn(d2, __fmul_rn(dot, n2));
-        float q = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(r0, r0), __fmul_rn(r1, r1)), __fmul_rn(r2, r2)));
+        const float q2 = __fadd_rn(__fadd_rn(__fmul_rn(r0, r0), __fmul_rn(r1, r1)), __fmul_rn(r2, r2));
+        const float q = q2 > 0.f ? sqrtf(q2) : 0.f;              // a point exactly on its ray: keep zero off sqrtf's slow path
         dmask = q < a.t_d ? 1.f : 0.f;
     }
 
@@ -144,7 +146,7 @@ __global__ void __launch_bounds__(NT) k_paste_front(PasteArgs a) {
     if (a.Rf > 0) {
         Tap tr = ortho_tap(vy, a.half_bw, a.inv_bw, a.Rf), tc = ortho_tap(vx, a.half_bw, a.inv_bw, a.Rf);
         const float* e = a.eroded + (size_t)n * a.Rf * a.Rf;
-        int r1 = min(tr.i0 + 1, a.Rf - 1), c1 = min(tc.i0 + 1, a.Rf - 1);         // weight is 0 where the neighbour is outside
+        const unsigned r1 = min(tr.i0 + 1, (unsigned)a.Rf - 1), c1 = min(tc.i0 + 1, (unsigned)a.Rf - 1);   // weight is 0 where the neighbour is outside
         float nw = (1.f - tr.f) * (1.f - tc.f), ne = tr.f * (1.f - tc.f), sw = (1.f - tr.f) * tc.f, se = tr.f * tc.f;
         fwmask = __ldg(e + tr.i0 * a.Rf + tc.i0) * nw + __ldg(e + r1 * a.Rf + tc.i0) * ne + __ldg(e + tr.i0 * a.Rf + c1) * sw +
                  __ldg(e + r1 * a.Rf + c1) * se;
@@ -153,19 +155,19 @@ __global__ void __launch_bounds__(NT) k_paste_front(PasteArgs a) {
 
     // paste + blend (:670-679); torch.lerp's two-sided formula
     Tap tr = ortho_tap(vy, a.half_bw, a.inv_bw, S), tc = ortho_tap(vx, a.half_bw, a.inv_bw, S);
-    int r1 = min(tr.i0 + 1, S - 1), c1 = min(tc.i0 + 1, S - 1);
+    const unsigned r1 = min(tr.i0 + 1, S - 1), c1 = min(tc.i0 + 1, S - 1);
     float nw = (1.f - tr.f) * (1.f - tc.f), ne = tr.f * (1.f - tc.f), sw = (1.f - tr.f) * tc.f, se = tr.f * tc.f;
     const size_t view3 = (size_t)n * 3 * plane;
     const float* fv = a.front + view3, *iv = a.image + view3;
     float* opv = a.o_paste + view3, *oiv = a.o_image + view3;
-    const int t00 = tr.i0 * S + tc.i0, t10 = r1 * S + tc.i0, t01 = tr.i0 * S + c1, t11 = r1 * S + c1;
+    const unsigned t00 = tr.i0 * S + tc.i0, t10 = r1 * S + tc.i0, t01 = tr.i0 * S + c1, t11 = r1 * S + c1;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    for (unsigned c = 0; c < 3; ++c) {
         const float* f = fv + c * plane;
         float f00 = __ldg(f + t00), f10 = __ldg(f + t10), f01 = __ldg(f + t01), f11 = __ldg(f + t11);
         if (a.normalize) { f00 = f00 * 2.f - 1.f; f10 = f10 * 2.f - 1.f; f01 = f01 * 2.f - 1.f; f11 = f11 * 2.f - 1.f; }
         float paste = f00 * nw + f10 * ne + f01 * sw + f11 * se;
-        const int o = c * plane + pix;
+        const unsigned o = c * plane + pix;
         float img = __ldg(iv + o);
         float diff = paste - img;
         opv[o] = paste;
@@ -174,7 +176,7 @@ __global__ void __launch_bounds__(NT) k_paste_front(PasteArgs a) {
     a.o_mask[(size_t)n * plane + pix] = mask;
     if (a.o_parts) {
         float* pv = a.o_parts + (size_t)n * plane;
-        const int st = a.N * plane;                                 // 5 * N * S * S < 2^31 (checked by the host)
+        const unsigned st = (unsigned)a.N * plane;                  // 5 * N * S * S < 2^31 (checked by the host)
         pv[pix] = wmask; pv[st + pix] = smask; pv[2 * st + pix] = fmask; pv[3 * st + pix] = dmask; pv[4 * st + pix] = fwmask;
     }
 }
