@@ -32,8 +32,8 @@ R, S, SF, P, C, VIEWS = 128, 96, 96, 512, 32, 8
 FLOP_PER_SAMPLE = 2 * 32 * 64 + 2 * 64 * 33            # 8,320 tensor-eligible FLOP
 BYTES_PER_VIEW = 3 * C * P * P * 4 + R * R * 37 * 4    # tri-plane read once + 37 floats/ray out
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the default fused kernel on this workload, from the committed
-# `ncu --set full` capture (profiles/r2_ws3_raw.csv)
-FUSED_TRAFFIC = 652.7e6
+# `ncu --set full` capture of the default bench command (profiles/r2_final_ws3_raw.csv: 632.8 MB read + 22.6 MB written)
+FUSED_TRAFFIC = 655.4e6
 
 
 # rendering_options of BASELINE configs[1] (train_eclustrousC.py:409-440 + eg3dc_v0.py:30-31,55-56)
