@@ -99,6 +99,8 @@ def main():
     ap.add_argument('--tiny', action='store_true', help='small channels / 16x16 rays (CPU smoke test of the harness)')
     ap.add_argument('--device', default='cuda:0')
     ap.add_argument('--reps', type=int, default=2, help='timed repetitions of the 16-view sweep')
+    ap.add_argument('--profile', help='write a per-kernel device-time table of one more sweep (torch.profiler / CUPTI) to this JSON file')
+    ap.add_argument('--reuse_triplane', action='store_true', help='ours arm: dropin.install_paste(reuse_triplane=True)')
     ap.add_argument('--paste', action='store_true', help="run the sweep with the eval script's paste_params (generate.py:59-65)")
     args = ap.parse_args()
     import torch
@@ -141,7 +143,7 @@ def main():
         installed = dropin.install()
     import training.triplane as tp
     if args.paste and args.arm == 'ours':
-        dropin.install_paste(tp)
+        dropin.install_paste(tp, reuse_triplane=args.reuse_triplane)
     mod_file = sys.modules[tp.ImportanceRenderer.__module__].__file__
     assert ('baseline/_ref' in mod_file.replace(os.sep, '/')) == (args.arm == 'reference'), mod_file
     G, R = build_generator(args, torch)
@@ -209,6 +211,21 @@ def main():
                 G.f(xin_for(e, a, f))
             dt = (time.perf_counter() - t0) * len(views) / 2 * args.reps
     vps = args.reps * len(views) / dt
+    if args.profile and dev.type == 'cuda':
+        try:                                                       # where a view's device time goes (the "next" row: backbone / SR kernels)
+            from torch.profiler import profile, ProfilerActivity
+            with torch.no_grad(), profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for (_cm, e, a, f) in views:
+                    G.f(xin_for(e, a, f))
+                torch.cuda.synchronize()
+            rows = sorted(((ev.key, ev.count, getattr(ev, 'device_time_total', getattr(ev, 'cuda_time_total', 0.0))) for ev in prof.key_averages()),
+                          key=lambda r: -r[2])
+            total = sum(r[2] for r in rows) or 1.0
+            json.dump({'arm': args.arm, 'views': len(views), 'device_ms_per_view': total / 1e3 / len(views),
+                       'kernels': [{'name': k[:160], 'launches': c, 'ms_per_view': t / 1e3 / len(views), 'share': t / total} for k, c, t in rows[:40]]},
+                      open(args.profile, 'w'), indent=1)
+        except Exception as e:                                     # profiling is evidence, not part of the measurement
+            print('profile failed:', repr(e), file=sys.stderr)
     res = {k: torch.cat(v) for k, v in {**outs, **pouts}.items()}
     res.update(arm=args.arm, views=views, views_per_s=vps, plane=args.plane)
     if args.out:

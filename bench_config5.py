@@ -40,6 +40,10 @@ def main():
     ap.add_argument('--iters', type=int, default=5)
     ap.add_argument('--tiny', action='store_true', help='small channels (CPU smoke test of the harness)')
     ap.add_argument('--device', default='cuda:0')
+    ap.add_argument('--paste', action='store_true',
+                    help="training mode 'Agrad' (loss_orthocondA.py:146-150): G.f pastes the front image with grad_sample=True, so Gmain "
+                         'back-propagates through paste_front into image_xyz; thresholds are permissive so that a random-weight generator '
+                         'yields a non-empty mask')
     args = ap.parse_args()
     sys.path.insert(0, ROOT)
     from baseline import ref_env
@@ -47,10 +51,16 @@ def main():
     import numpy as np
     import torch
     dev = torch.device(args.device)
+    if args.paste and args.arm == 'reference':
+        from oracle.paste_oracle import kornia_shim               # reference arm only: the two kornia calls of ITS paste_front
+        k = kornia_shim()
+        sys.modules['kornia'], sys.modules['kornia.filters'], sys.modules['kornia.morphology'] = k, k.filters, k.morphology
     if args.arm == 'ours':
         import panic3d_b200.dropin as dropin
         dropin.install()
     import training.triplane as tp
+    if args.paste and args.arm == 'ours':
+        dropin.install_paste(tp)
     from training.dual_discriminator import DualDiscriminator
     from torch_utils.ops import conv2d_gradfix
     conv2d_gradfix.enabled = True                               # training_loop_v0.py:143
@@ -86,11 +96,22 @@ def main():
     real['image_raw'] = torch.nn.functional.interpolate(real['image'], size=(R, R), mode='bilinear', antialias=True)
     cond = {}
     gain, r1_gamma = 1.0, 1.0
+    # training mode 'Agrad': paste_params with grad_sample=True (loss_orthocondA.py:131-150); the thresholds of that mode select nothing
+    # on a random-weight generator (cf. profiles/r2_configs/c3p_compare.json), so the harness opens them up: mask = (weights > 0.5)
+    paste_params = ({'mode': 'default', 'thresh_weight': 0.5, 'thresh_edges': 0.5, 'thresh_occ': 2.0, 'offset_occ': 0.01, 'thresh_dxyz': 10.0,
+                     'grad_sample': True} if args.paste else None)
+    lin = torch.linspace(0, 1, res)
+    yy, xx = torch.meshgrid(lin, lin, indexing='ij')                # a smooth front image: the lookup's gradient is then smooth in xyz,
+    front = torch.stack([0.5 + 0.5 * torch.sin(6 * xx + ch) * torch.cos(5 * yy - ch) for ch in range(3)])   # so the arms' different jitter barely moves it
+    g_cond = {'image_ortho_front': front[None].repeat(B, 1, 1, 1).to(dev)} if args.paste else cond
+    last = {}
 
     def run_G(update_emas=False):
         ws = G.mapping(gen_z, torch.zeros_like(gen_c), cond, update_emas=update_emas)
-        out = G.f({'ws': ws, 'camera_params': gen_c, 'cond': cond, 'normalize_images': True, 'neural_rendering_resolution': R,
-                   'update_emas': update_emas, 'paste_params': None})
+        out = G.f({'ws': ws, 'camera_params': gen_c, 'cond': g_cond, 'normalize_images': True, 'neural_rendering_resolution': R,
+                   'update_emas': update_emas, 'paste_params': paste_params})
+        if paste_params is not None:
+            last['mask_mean'] = float(out['paste']['mask'].mean())
         return out, ws
 
     def run_D(img, c):
@@ -165,6 +186,8 @@ def main():
             'ms': {n: (statistics.median(v) if v else None) for n, v in times.items()},
             'ms_total': (sum(statistics.median(v) for v in times.values()) if cuda else None),
             'renderer_module': mod_file.replace(ROOT, '.'), 'grads': gstat}
+    if args.paste:
+        line['paste'] = {'params': paste_params, 'mask_mean': last.get('mask_mean')}
     if args.arm == 'ours':
         from panic3d_b200 import _lib
         line['gpu_launches'] = _lib.launch_count()

@@ -57,13 +57,16 @@ def install(renderer: bool = True, ops: bool = True, strict: bool = False):
     return done
 
 
-def install_paste(module=None):
+def install_paste(module=None, reuse_triplane=False):
     """Rebind the reference's ``paste_front`` (``training/triplane.py:608-691``) and its two render helpers
     to the fused implementation in ``panic3d_b200.paste``.  ``G.f`` looks ``paste_front`` up in its own module's globals
     at call time (triplane.py:498-502), so setting the attribute on that module is the whole plug-in: no caller edits.
     ``module``: the reference's already-imported ``training.triplane`` (default: import it by that name).
+    ``reuse_triplane=True``: the occlusion render of ``paste_front`` is rendered from ``out['triplane']`` instead of a second full
+    ``G.f`` (backbone + super-resolution re-run for nothing) - a documented deviation, see ``paste.REUSE_TRIPLANE``.
     Returns the names that were rebound."""
     from . import paste
+    paste.REUSE_TRIPLANE = bool(reuse_triplane)
     if module is None:
         module = importlib.import_module('training.triplane')
     names = ['paste_front', 'get_front_occlusion', 'get_front_weights']

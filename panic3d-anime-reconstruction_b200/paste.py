@@ -89,9 +89,25 @@ def occlusion_rays(image_xyz, ray_start, offset=0.01):
     return ro, rd
 
 
+# Opt-in (``dropin.install_paste(reuse_triplane=True)``): the occlusion render needs only ``image_weights``, and ``G.f`` hands the
+# tri-planes of the view back in ``out['triplane']`` (triplane.py:233-240) - so render from them directly instead of going through
+# ``G.f`` again, which re-runs the 29 M-parameter backbone and the super-resolution head just to throw their outputs away.
+# A deliberate deviation, like the plane memo: the reference's second ``G.f`` redraws the backbone's layer noise (noise_mode defaults
+# to 'random', networks_stylegan2.py:334-343), so ITS occlusion render sees slightly different tri-planes than the view it belongs to;
+# with const / no noise the two routes give the same weights.  Off by default.
+REUSE_TRIPLANE = False
+
+
 def get_front_occlusion(G, x, out, offset=0.01):
     """triplane.py:565-580: render along +z from the visible surface; returns that render's ``image_weights``."""
     ro, rd = occlusion_rays(out['image_xyz'], G.rendering_kwargs['ray_start'], offset)
+    if REUSE_TRIPLANE and out.get('triplane') is not None and hasattr(G, 'renderer'):
+        N, _, R, _ = ro.shape
+        flat = lambda t: t.permute(0, 2, 3, 1).reshape(N, R * R, 3)
+        _, _, weights, _ = G.renderer(out['triplane'], G.decoder, flat(ro), flat(rd), G.rendering_kwargs,
+                                      triplane_crop=x.get('triplane_crop'), cull_clouds=x.get('cull_clouds'),
+                                      binarize_clouds=x.get('binarize_clouds'))
+        return weights.permute(0, 2, 1).reshape(N, 1, R, R)
     xin = {**x}
     xin['paste_params'] = None
     xin['force_rays'] = {'ray_origins': ro, 'ray_directions': rd}

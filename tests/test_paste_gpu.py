@@ -157,3 +157,35 @@ def test_gradients_match_oracle_autograd(grad_sample):
         out = pp.paste_front_fused(image3, d['image_xyz'], d['image_weights'], d['front_rgb'], d['occ'], d['ro'], d['rd'], 0.7)[0]
         (gi,) = torch.autograd.grad(out.sum(), image3, create_graph=True)
         gi.sum().backward()
+
+
+def test_reuse_triplane_renders_the_occlusion_pass_from_the_views_planes():
+    """Opt-in route of get_front_occlusion: G.renderer on out['triplane'] instead of a second G.f."""
+    import panic3d_b200.paste as pp
+    inp = po.synth_paste_inputs(9, 2, 12, 24)
+    calls = {}
+
+    class G:
+        rendering_kwargs = {'ray_start': 0.5, 'box_warp': 0.7}
+        decoder = object()
+
+        @staticmethod
+        def renderer(planes, decoder, ro, rd, opts, **flags):
+            calls.update(planes=planes, ro=ro, rd=rd, flags=flags)
+            n, m, _ = ro.shape
+            return None, None, torch.arange(n * m, device=ro.device, dtype=torch.float32).reshape(n, m, 1), None
+
+        @staticmethod
+        def f(*a, **k):
+            raise AssertionError('G.f must not be called when the tri-planes are reused')
+
+    out = {'image_xyz': inp['image_xyz'].to(DEV), 'triplane': torch.zeros(2, 3, 32, 8, 8, device=DEV)}
+    pp.REUSE_TRIPLANE = True
+    try:
+        w = pp.get_front_occlusion(G, {'triplane_crop': 0.1, 'cull_clouds': 0.5}, out, offset=0.01)
+    finally:
+        pp.REUSE_TRIPLANE = False
+    o_ro, o_rd = po.occlusion_rays(inp['image_xyz'], 0.5, 0.01)
+    assert torch.equal(calls['ro'].cpu(), o_ro.permute(0, 2, 3, 1).reshape(2, 144, 3)) and torch.equal(calls['rd'].cpu(), o_rd.permute(0, 2, 3, 1).reshape(2, 144, 3))
+    assert calls['planes'] is out['triplane'] and calls['flags'] == {'triplane_crop': 0.1, 'cull_clouds': 0.5, 'binarize_clouds': None}
+    assert tuple(w.shape) == (2, 1, 12, 12) and torch.equal(w.flatten().cpu(), torch.arange(288, dtype=torch.float32))
