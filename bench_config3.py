@@ -100,6 +100,7 @@ def main():
     ap.add_argument('--device', default='cuda:0')
     ap.add_argument('--reps', type=int, default=2, help='timed repetitions of the 16-view sweep')
     ap.add_argument('--profile', help='write a per-kernel device-time table of one more sweep (torch.profiler / CUPTI) to this JSON file')
+    ap.add_argument('--graphs', action='store_true', help='ours arm: panic3d_b200.graphs.enable_cuda_graphs(G) - backbone and SR head replayed as CUDA graphs')
     ap.add_argument('--reuse_triplane', action='store_true', help='ours arm: dropin.install_paste(reuse_triplane=True)')
     ap.add_argument('--paste', action='store_true', help="run the sweep with the eval script's paste_params (generate.py:59-65)")
     args = ap.parse_args()
@@ -148,6 +149,10 @@ def main():
     assert ('baseline/_ref' in mod_file.replace(os.sep, '/')) == (args.arm == 'reference'), mod_file
     G, R = build_generator(args, torch)
     G = G.to(dev)
+    graphed = None
+    if args.graphs and args.arm == 'ours' and dev.type == 'cuda':
+        from panic3d_b200 import graphs
+        graphed = graphs.enable_cuda_graphs(G)
     views = sweep_views()
     ws = None
     S = int(G.rendering_kwargs['depth_resolution'])
@@ -211,6 +216,30 @@ def main():
                 G.f(xin_for(e, a, f))
             dt = (time.perf_counter() - t0) * len(views) / 2 * args.reps
     vps = args.reps * len(views) / dt
+    graph_report = None
+    if graphed:
+        # self-check: the first views again with the graphs taken out (deterministic pass) must reproduce the graphed outputs
+        with torch.no_grad():
+            saved = {n: w_ for n, w_ in graphed.items()}
+            mods = {'backbone': G.backbone.synthesis, 'superresolution': G.superresolution}
+            for n, w_ in saved.items():
+                mods[n].forward = w_.fn
+            fwd = G.backbone.synthesis.forward
+            G.backbone.synthesis.forward = lambda *a, **k: fwd(*a, **dict(k, noise_mode='const'))
+            gen = torch.Generator().manual_seed(123)
+            worst = 0.0
+            for i, (_cm, e, a, f) in enumerate(views[:4]):
+                u_c = torch.rand(1, R * R, S, 1, generator=gen)
+                u_f = torch.rand(R * R, Sf, generator=gen)
+                G.renderer.injected_noise = (u_c, u_f)
+                out = G.f(xin_for(e, a, f))
+                G.renderer.injected_noise = None
+                worst = max(worst, float((out['image'].float().cpu() - outs['image'][i]).abs().max()))
+            G.backbone.synthesis.forward = fwd
+            for n, w_ in saved.items():
+                mods[n].forward = w_
+        graph_report = {'eager_vs_graph_max_abs_image': worst,
+                        **{n: {'captures': w_.captures, 'replays': w_.hits, 'bypassed': w_.bypassed, 'failed_signatures': len(w_.failed)} for n, w_ in graphed.items()}}
     if args.profile and dev.type == 'cuda':
         try:                                                       # where a view's device time goes (the "next" row: backbone / SR kernels)
             from torch.profiler import profile, ProfilerActivity
@@ -237,6 +266,8 @@ def main():
     if args.arm == 'ours':
         from panic3d_b200 import _lib
         line['gpu_launches'] = _lib.launch_count()
+    if graph_report:
+        line['cuda_graphs'] = graph_report
     print(json.dumps(line))
 
 
