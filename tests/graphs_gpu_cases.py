@@ -1,4 +1,4 @@
-"""Bodies of tests/test_graphs_gpu.py - each runs in its own interpreter (a capture that is made to fail must not be able to
+"""Bodies of tests/test_zz_graphs_gpu.py - each runs in its own interpreter (a capture that is made to fail must not be able to
 disturb the CUDA context the rest of the GPU suite shares)."""
 import os
 import sys
@@ -20,7 +20,10 @@ class Net(torch.nn.Module):
         super().__init__()
         self.c1 = torch.nn.Conv2d(3, 8, 3, padding=1)
         self.c2 = torch.nn.Conv2d(8, 3, 3, padding=1)
-        self.register_buffer('f', torch.tensor([1., 3., 3., 1.]))
+        from panic3d_b200.torch_utils.ops import upfirdn2d
+        self.register_buffer('f', upfirdn2d.setup_filter([1, 3, 3, 1]))          # like the networks: filters are buffers, built once
+                                                                                 # (setup_filter inside forward = a host->device copy per call,
+                                                                                 #  which no capture allows - the wrapper then stays eager)
 
     def forward(self, x, cond, noise_mode='random'):
         from panic3d_b200.torch_utils.ops import bias_act, upfirdn2d
@@ -28,7 +31,7 @@ class Net(torch.nn.Module):
         if noise_mode == 'random':
             h = h + torch.randn([x.shape[0], 1, x.shape[2], x.shape[3]], device=x.device) * 0.1
         h = bias_act.bias_act(h, self.c1.bias, act='lrelu')
-        h = upfirdn2d.upsample2d(h, upfirdn2d.setup_filter([1, 3, 3, 1], device=x.device))
+        h = upfirdn2d.upsample2d(h, self.f)
         return self.c2(h), {'feat': h}
 
 
