@@ -63,8 +63,9 @@ class _Entry:
 class GraphedCallable:
     """See the module docstring.  ``hits`` / ``captures`` / ``bypassed`` count what happened to the calls."""
 
-    def __init__(self, fn, name='callable', warmup=3, max_entries=8):
+    def __init__(self, fn, name='callable', warmup=3, max_entries=8, lean_return_more=False):
         self.fn, self.name, self.warmup, self.max_entries = fn, name, warmup, max_entries
+        self.lean_return_more = lean_return_more
         self.entries = {}
         self.failed = set()
         self.hits = self.captures = self.bypassed = 0
@@ -90,6 +91,10 @@ class GraphedCallable:
         return e
 
     def __call__(self, *args, **kwargs):
+        if self.lean_return_more and kwargs.get('return_more'):
+            # opt-in: the reference's return_more route hands back `locals()` next to the result (networks_stylegan2.py:715-718), which
+            # only debugging code reads; replay the graph of the plain call and return an empty dict in its place
+            return self(*args, **{k: v for k, v in kwargs.items() if k != 'return_more'}), {}
         tensors = []
         try:
             key = _flatten((list(args), kwargs), tensors)
@@ -126,8 +131,11 @@ class GraphedCallable:
             return _rebuild(e.out_obj, [t.clone() for t in e.static_out], [0])
 
 
-def enable_cuda_graphs(G, backbone=True, superresolution=True):
+def enable_cuda_graphs(G, backbone=True, superresolution=True, lean_return_more=False):
     """Put a ``GraphedCallable`` in front of ``G.backbone.synthesis.forward`` and ``G.superresolution.forward``; idempotent.
+    ``lean_return_more=True``: backbone calls with ``return_more=True`` (what ``G.f(x, return_more=True)`` issues, e.g.
+    ``_scripts/eval/generate.py:130``) are replayed too and return ``(planes, {})`` instead of ``(planes, locals())`` - a deliberate
+    deviation for callers that never look at the backbone's locals; off by default (such calls then stay eager).
     Returns {'backbone': wrapper, 'superresolution': wrapper} (``.hits`` / ``.captures`` / ``.bypassed``).  Compose with
     ``dropin.enable_plane_reuse`` in either order (the memo then skips the backbone graph's replay on repeated latents)."""
     out = {}
@@ -139,7 +147,7 @@ def enable_cuda_graphs(G, backbone=True, superresolution=True):
     for name, mod in targets:
         wrapper = getattr(mod, '_p3d_graphed', None)
         if wrapper is None:
-            wrapper = GraphedCallable(mod.forward, name=name)
+            wrapper = GraphedCallable(mod.forward, name=name, lean_return_more=lean_return_more and name == 'backbone')
             mod.forward = wrapper
             mod._p3d_graphed = wrapper
         out[name] = wrapper

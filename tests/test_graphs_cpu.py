@@ -59,3 +59,17 @@ def test_enable_is_idempotent_and_keeps_module_state():
     assert list(m.state_dict()) == keys
     x = torch.randn(2, 3)
     assert torch.equal(m.backbone.synthesis(x), w1['backbone'].fn(x))     # CPU call goes straight through
+
+
+def test_lean_return_more_replaces_locals_with_an_empty_dict():
+    def fn(x, return_more=False):
+        return (x + 1, locals()) if return_more else x + 1
+
+    x = torch.zeros(3)
+    keep = graphs.GraphedCallable(fn)
+    y, loc = keep(x, return_more=True)
+    assert torch.equal(y, x + 1) and 'x' in loc                      # default: the reference's behaviour, eager
+    lean = graphs.GraphedCallable(fn, lean_return_more=True)
+    y, loc = lean(x, return_more=True)
+    assert torch.equal(y, x + 1) and loc == {}
+    assert torch.equal(lean(x), x + 1)
