@@ -136,8 +136,9 @@ def enable_cuda_graphs(G, backbone=True, superresolution=True, lean_return_more=
     ``lean_return_more=True``: backbone calls with ``return_more=True`` (what ``G.f(x, return_more=True)`` issues, e.g.
     ``_scripts/eval/generate.py:130``) are replayed too and return ``(planes, {})`` instead of ``(planes, locals())`` - a deliberate
     deviation for callers that never look at the backbone's locals; off by default (such calls then stay eager).
-    Returns {'backbone': wrapper, 'superresolution': wrapper} (``.hits`` / ``.captures`` / ``.bypassed``).  Compose with
-    ``dropin.enable_plane_reuse`` in either order (the memo then skips the backbone graph's replay on repeated latents)."""
+    Returns {'backbone': wrapper, 'superresolution': wrapper} (``.hits`` / ``.captures`` / ``.bypassed``).  Composes with
+    ``dropin.enable_plane_reuse`` in either order: the graph always ends up underneath the memo, which then skips the replay
+    on repeated latents."""
     out = {}
     targets = []
     if backbone and hasattr(G, 'backbone') and isinstance(getattr(G.backbone, 'synthesis', None), torch.nn.Module):
@@ -147,8 +148,13 @@ def enable_cuda_graphs(G, backbone=True, superresolution=True, lean_return_more=
     for name, mod in targets:
         wrapper = getattr(mod, '_p3d_graphed', None)
         if wrapper is None:
-            wrapper = GraphedCallable(mod.forward, name=name, lean_return_more=lean_return_more and name == 'backbone')
-            mod.forward = wrapper
+            memo = getattr(mod, '_p3d_plane_memo', None)          # dropin.enable_plane_reuse was here first: the graph goes UNDER the
+            if memo is not None:                                  # memo (its value comparison of the latents is a host sync no capture allows)
+                wrapper = GraphedCallable(memo.synthesis, name=name, lean_return_more=lean_return_more and name == 'backbone')
+                memo.synthesis = wrapper
+            else:
+                wrapper = GraphedCallable(mod.forward, name=name, lean_return_more=lean_return_more and name == 'backbone')
+                mod.forward = wrapper
             mod._p3d_graphed = wrapper
         out[name] = wrapper
     return out

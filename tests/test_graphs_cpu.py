@@ -73,3 +73,32 @@ def test_lean_return_more_replaces_locals_with_an_empty_dict():
     y, loc = lean(x, return_more=True)
     assert torch.equal(y, x + 1) and loc == {}
     assert torch.equal(lean(x), x + 1)
+
+
+def test_composes_with_the_plane_memo_in_either_order():
+    import panic3d_b200.dropin as dropin
+
+    class Syn(torch.nn.Module):
+        def forward(self, ws, cond=None, **kw):
+            return ws * 2
+
+    def make():
+        g = torch.nn.Module()
+        g.backbone = torch.nn.Module()
+        g.backbone.synthesis = Syn()
+        return g
+
+    ws = torch.ones(1, 4)
+    a = make()
+    memo = dropin.enable_plane_reuse(a)
+    w = graphs.enable_cuda_graphs(a, superresolution=False)['backbone']
+    assert a.backbone.synthesis.forward is memo and memo.synthesis is w        # graph underneath the memo
+    b = make()
+    w2 = graphs.enable_cuda_graphs(b, superresolution=False)['backbone']
+    memo2 = dropin.enable_plane_reuse(b)
+    assert b.backbone.synthesis.forward is memo2 and memo2.synthesis is w2
+    for g_, m_ in ((a, memo), (b, memo2)):
+        with torch.no_grad():
+            assert torch.equal(g_.backbone.synthesis(ws, None, noise_mode='const'), ws * 2)
+            assert torch.equal(g_.backbone.synthesis(ws, None, noise_mode='const'), ws * 2)
+        assert m_.hits == 1 and m_.misses == 1
