@@ -1,4 +1,10 @@
-"""Drop-in for ``torch_utils/ops/upfirdn2d.py`` (reference ops/upfirdn2d.py:37-389).
+"""Host mirror of ``torch_utils/ops/upfirdn2d.py`` (reference ops/upfirdn2d.py:37-389).
+
+Interface contract, not an implementation: the argument-parsing helpers (``_parse_scaling``, ``_parse_padding``,
+``_get_filter_size``), ``setup_filter`` and the padding arithmetic of ``filter2d`` / ``upsample2d`` / ``downsample2d`` below follow
+the reference line for line because other reference modules import those private names (``conv2d_resample.py``,
+``networks_stylegan2.py``) and any other arithmetic would change output sizes; everything that does work - the kernels, the autograd
+formulation - is this repository's own.
 
 Same public names and argument meaning - ``setup_filter``, ``upfirdn2d``, ``filter2d``, ``upsample2d``,
 ``downsample2d`` (+ the ``_parse_*`` / ``_get_filter_size`` helpers other reference modules import) - over the
