@@ -50,6 +50,16 @@ def test_reference_generator_uses_dropin_modules():
         assert type(G.ray_sampler) is ours_s.RaySampler
         assert sum(p.numel() for p in G.renderer.parameters()) == 0
         assert tuple(G.decoder.net[0].weight.shape) == (64, 32) and tuple(G.decoder.net[2].weight.shape) == (33, 64)
+        # SURVEY 8f-3: G.f resolves `paste_front` in its module's globals at call time (triplane.py:498-502), so rebinding the
+        # module attribute is the whole plug-in
+        import inspect
+        import panic3d_b200.paste as ours_p
+        ref_paste = tp.paste_front
+        assert 'paste = paste_front(self, x, ret, **x[' in inspect.getsource(tp.TriPlaneGenerator.f)
+        assert d.install_paste() == ['paste_front', 'get_front_occlusion', 'get_front_weights']     # finds training.triplane by name
+        assert tp.paste_front is ours_p.paste_front and tp._p3d_reference_paste_front is ref_paste
+        assert tp.TriPlaneGenerator.f.__globals__['paste_front'] is ours_p.paste_front
+        assert list(inspect.signature(ours_p.paste_front).parameters)[:12] == list(inspect.signature(ref_paste).parameters)[:12]
         print('ok')
     ''' % dict(root=ROOT, ref=REF))
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
