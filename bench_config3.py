@@ -100,6 +100,9 @@ def main():
     ap.add_argument('--device', default='cuda:0')
     ap.add_argument('--reps', type=int, default=2, help='timed repetitions of the 16-view sweep')
     ap.add_argument('--profile', help='write a per-kernel device-time table of one more sweep (torch.profiler / CUPTI) to this JSON file')
+    ap.add_argument('--save', help='ours arm: write every view of the timed sweep as PNGs into this directory through panic3d_b200.imageio.AsyncImageWriter '
+                                   '(generate.py:141-148), flush inside the timed region')
+    ap.add_argument('--return_more', action='store_true', help='call G.f(x, return_more=True) like generate.py:130 (with --graphs: lean_return_more)')
     ap.add_argument('--graphs', action='store_true', help='ours arm: panic3d_b200.graphs.enable_cuda_graphs(G) - backbone and SR head replayed as CUDA graphs')
     ap.add_argument('--reuse_triplane', action='store_true', help='ours arm: dropin.install_paste(reuse_triplane=True)')
     ap.add_argument('--paste', action='store_true', help="run the sweep with the eval script's paste_params (generate.py:59-65)")
@@ -152,7 +155,7 @@ def main():
     graphed = None
     if args.graphs and args.arm == 'ours' and dev.type == 'cuda':
         from panic3d_b200 import graphs
-        graphed = graphs.enable_cuda_graphs(G)
+        graphed = graphs.enable_cuda_graphs(G, lean_return_more=args.return_more)
     views = sweep_views()
     ws = None
     S = int(G.rendering_kwargs['depth_resolution'])
@@ -204,12 +207,28 @@ def main():
             for (_cm, e, a, f) in views[:3]:
                 G.f(xin_for(e, a, f))
             torch.cuda.synchronize()
+            writer = None
+            if args.save and args.arm == 'ours':
+                import panic3d_b200.imageio as pio
+                os.makedirs(args.save, exist_ok=True)
+                writer = pio.AsyncImageWriter(threads=8, level=3)
+                writer.save(G.f(xin_for(*views[0][1:]))['image'], os.path.join(args.save, 'warm.png')); writer.flush()
+            bw = G.rendering_kwargs['box_warp']
+            fkw = {'return_more': True} if args.return_more else {}
             t0 = time.perf_counter()
-            for _ in range(args.reps):
-                for (_cm, e, a, f) in views:
-                    G.f(xin_for(e, a, f))
+            for rep in range(args.reps):
+                for i, (_cm, e, a, f) in enumerate(views):
+                    out = G.f(xin_for(e, a, f), **fkw)
+                    if writer is not None:
+                        writer.save(out['image'], os.path.join(args.save, f'rgb_{rep}_{i:02d}.png'))
+                        writer.save_xyza(out['image_xyz'], out['image_weights'], bw, os.path.join(args.save, f'xyza_{rep}_{i:02d}.png'))
+            if writer is not None:
+                writer.flush()
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
+            if writer is not None:
+                n_files = len([f_ for f_ in os.listdir(args.save) if f_.endswith('.png')])
+                writer.close()
         else:
             t0 = time.perf_counter()
             for (_cm, e, a, f) in views[:2]:
@@ -268,6 +287,10 @@ def main():
         line['gpu_launches'] = _lib.launch_count()
     if graph_report:
         line['cuda_graphs'] = graph_report
+    if args.save and args.arm == 'ours' and dev.type == 'cuda':
+        line['saved_png_files'] = n_files
+    if args.return_more:
+        line['return_more'] = True
     print(json.dumps(line))
 
 
