@@ -112,7 +112,8 @@ class GraphedCallable:
                 self.bypassed += 1
                 return self.fn(*args, **kwargs)
             try:
-                e = self._capture(args, kwargs, tensors)
+                with torch.cuda.device(tensors[0].device):      # capture on the tensors' device, whatever the caller's current one is
+                    e = self._capture(args, kwargs, tensors)
             except Exception as err:                         # this signature stays eager; say so once
                 self.failed.add(key)
                 torch.cuda.synchronize()
@@ -122,7 +123,7 @@ class GraphedCallable:
                 return self.fn(*args, **kwargs)
             self.entries[key] = e
             self.captures += 1
-        with torch.no_grad():
+        with torch.no_grad(), torch.cuda.device(tensors[0].device):
             for dst, src in zip(e.static_in, tensors):
                 if dst.data_ptr() != src.data_ptr():
                     dst.copy_(src)
